@@ -1,0 +1,478 @@
+// lcu_program.cpp -- object loading, program assembly, NVRTC build, metadata.
+//
+// Replaces the reference's src/kernel.c (load_object :731-816, main_program
+// :838-879, compute_kernel :235-399, set_params_kernel :401-656,
+// kernel_options :881-944) and the metadata round trip of
+// src/input/objects.c:72-239.  Same contract for object files; different
+// mechanics: C++ instead of OpenCL C, NVRTC instead of clBuildProgram, and
+// metadata read from the compiled module instead of from meta kernels.
+
+#include "lcu_internal.h"
+
+#include <nvrtc.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <regex>
+#include <sstream>
+
+namespace lcu {
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1 << 16];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+const char* get_error() { return g_error.c_str(); }
+
+// ---------------------------------------------------------------------------
+// text utilities
+// ---------------------------------------------------------------------------
+std::string read_text_file(const std::string& path, bool* ok)
+{
+    std::ifstream f(path, std::ios::binary);
+    if(!f)
+    {
+        *ok = false;
+        return std::string();
+    }
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    *ok = true;
+    return ss.str();
+}
+
+// OpenCL vector literals "(float2)(a, b)" are a cast applied to a comma
+// expression in C++; rewrite them to constructor calls "float2(a, b)".
+std::string rewrite_literals(const std::string& text)
+{
+    static const std::regex lit(R"(\(\s*(float2|float4|mat22)\s*\)\s*\()");
+    return std::regex_replace(text, lit, "$1(");
+}
+
+// object names go into identifiers (type_<name>, data_<name>, ...); the
+// reference pastes them verbatim (src/kernel.c:153-162), which cannot work for
+// names like "sersic-old"; here every non-identifier character becomes '_'
+std::string make_ident(const std::string& name)
+{
+    std::string id = name;
+    for(char& c : id)
+        if(!((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'))
+            c = '_';
+    return id;
+}
+
+// The name-mangling wrapper of src/kernel.c:153-172 (OBJHEAD / OBJFOOT), plus
+// the metadata export that replaces the meta_<name> / params_<name> kernels
+// of src/kernel.c:41-62: type, sizeof(data) and the parameter count become an
+// initialised device array the host reads back from the module image.
+std::string wrap_object(const std::string& name, const std::string& id, const std::string& text)
+{
+    std::ostringstream s;
+    s << "//----------------------------------------------------------------------------\n"
+      << "// objects/" << name << ".cl\n"
+      << "//----------------------------------------------------------------------------\n"
+      << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
+      << "#define type const int type_" << id << "\n"
+      << "#define params extern \"C\" __device__ const struct param lcu_parlst_" << id << "[] = \n"
+      << "#define data struct data_" << id << "\n"
+      << "#define deflection deflection_" << id << "\n"
+      << "#define brightness brightness_" << id << "\n"
+      << "#define foreground foreground_" << id << "\n"
+      << "#define set set_" << id << "\n"
+      << "#line 1 \"objects/" << name << ".cl\"\n"
+      << rewrite_literals(text) << "\n"
+      << "#undef type\n#undef params\n#undef data\n#undef deflection\n"
+      << "#undef brightness\n#undef foreground\n#undef set\n"
+      << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
+      << "extern \"C\" __device__ const unsigned int lcu_meta_" << id << "[3] = {\n"
+      << "    (unsigned int)type_" << id << ",\n"
+      << "    (unsigned int)sizeof(struct data_" << id << "),\n"
+      << "    (unsigned int)(sizeof(lcu_parlst_" << id << ")/sizeof(struct param))\n"
+      << "};\n\n";
+    return s.str();
+}
+
+// ---------------------------------------------------------------------------
+// generated device functions
+// ---------------------------------------------------------------------------
+static const char* DEFLECT =
+    " -= dot(a, a) < HUGE_VALF ? a : lcu_float2(1E10f, 1E10f);\n";
+
+// compute(): src/kernel.c:65-111 templates, :321-383 object loop.  Objects are
+// visited in ini order.  A change of the (non-foreground) object type away
+// from LENS closes the lens plane: the summed deflection is applied to the
+// ray if finite.  Sources see the ray position y, foregrounds the image-plane
+// position x.
+std::string generate_compute(const std::vector<ModelObject>& objs)
+{
+    std::ostringstream s;
+    s << "__device__ __forceinline__ float lcu_compute(const uint* data, lcu_float2 x)\n{\n"
+      << "    lcu_float2 y = x;\n"
+      << "    float f = 0;\n";
+    int type = 0, trigger = 0;
+    bool open = false;
+    for(const ModelObject& o : objs)
+    {
+        const int t = o.info->type;
+        const std::string& id = o.info->ident;
+        if(t != trigger && t != LCU_FOREGROUND)
+        {
+            if(trigger == LCU_LENS)
+            {
+                s << "        y" << DEFLECT << "    }\n";
+                open = false;
+            }
+            trigger = t;
+        }
+        if(t != type)
+        {
+            if(t == LCU_LENS && !open)
+            {
+                s << "    {\n        lcu_float2 a = 0;\n";
+                open = true;
+            }
+            type = t;
+        }
+        const char* ind = open ? "        " : "    ";
+        if(t == LCU_LENS)
+            s << ind << "a += deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+        else if(t == LCU_SOURCE)
+            s << ind << "f += brightness_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+        else
+            s << ind << "f += foreground_" << id << "((struct data_" << id << "*)(data + " << o.d << "), x);\n";
+    }
+    if(trigger == LCU_LENS)
+        s << "        y" << DEFLECT << "    }\n";
+    s << "    return f;\n}\n\n";
+    return s.str();
+}
+
+// set_params(): src/kernel.c:114-150 templates, :455-633 object loop.  Each
+// object's setter receives its parameters in declaration order; a position
+// pair with image-plane priors is first shot through every lens in front of
+// the current source plane (src/kernel.c:499-564).
+std::string generate_set_params(const std::vector<ModelObject>& objs)
+{
+    std::ostringstream s;
+    s << "__device__ __forceinline__ void lcu_set_params_body(uint* data, const float* params)\n{\n"
+      << "    lcu_float2 x = 0;\n"
+      << "    lcu_float2 a = 0;\n";
+    int trigger = 0;
+    size_t plane = 0;
+    for(size_t i = 0; i < objs.size(); ++i)
+    {
+        const ModelObject& o = objs[i];
+        const int t = o.info->type;
+        const std::string& id = o.info->ident;
+        if(t != trigger && t != LCU_FOREGROUND)
+        {
+            if(trigger == LCU_LENS && t == LCU_SOURCE)
+                plane = i;
+            trigger = t;
+        }
+        for(size_t j = 0; j < o.info->params.size(); ++j)
+        {
+            if(!o.ipp[j] || o.info->params[j].type != LCU_POSITION_X)
+                continue;
+            int trigger2 = 0;
+            s << "    x = lcu_float2(params[" << (o.p + j) << "], params[" << (o.p + j + 1) << "]);\n";
+            for(size_t k = 0; k < plane; ++k)
+            {
+                const ModelObject& l = objs[k];
+                if(l.info->type != trigger2 && l.info->type != LCU_FOREGROUND)
+                {
+                    if(trigger2 == LCU_LENS)
+                        s << "    x" << DEFLECT << "    a = 0;\n";
+                    trigger2 = l.info->type;
+                }
+                if(l.info->type == LCU_LENS)
+                    s << "    a += deflection_" << l.info->ident << "((struct data_" << l.info->ident
+                      << "*)(data + " << l.d << "), x);\n";
+            }
+            if(trigger2 == LCU_LENS)
+                s << "    x" << DEFLECT << "    a = 0;\n";
+        }
+        s << "    set_" << id << "((struct data_" << id << "*)(data + " << o.d << ")";
+        for(size_t j = 0; j < o.info->params.size(); ++j)
+        {
+            if(o.ipp[j])
+            {
+                const int pt = o.info->params[j].type;
+                s << ", " << (pt == LCU_POSITION_X ? "x.x" : pt == LCU_POSITION_Y ? "x.y" : "0");
+            }
+            else
+                s << ", params[" << (o.p + j) << "]";
+        }
+        s << ");\n";
+    }
+    s << "    (void)x; (void)a;\n}\n\n";
+    return s.str();
+}
+
+// ---------------------------------------------------------------------------
+// NVRTC
+// ---------------------------------------------------------------------------
+bool compile_cubin(const std::string& source, const std::vector<Header>& headers,
+                   const std::vector<std::string>& options,
+                   std::vector<char>* cubin, std::string* log)
+{
+    nvrtcProgram prog = nullptr;
+    std::vector<const char*> hsrc, hname;
+    for(const Header& h : headers)
+    {
+        hname.push_back(h.first.c_str());
+        hsrc.push_back(h.second.c_str());
+    }
+    nvrtcResult r = nvrtcCreateProgram(&prog, source.c_str(), "lensed_model.cu", (int)headers.size(),
+                                       hsrc.data(), hname.data());
+    if(r != NVRTC_SUCCESS)
+    {
+        *log = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
+        return false;
+    }
+    std::vector<const char*> opts;
+    for(const std::string& o : options)
+        opts.push_back(o.c_str());
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    if(n > 1)
+    {
+        log->resize(n);
+        nvrtcGetProgramLog(prog, &(*log)[0]);
+    }
+    else
+        log->clear();
+    if(r != NVRTC_SUCCESS)
+    {
+        *log = std::string("nvrtcCompileProgram: ") + nvrtcGetErrorString(r) + "\n" + *log;
+        nvrtcDestroyProgram(&prog);
+        return false;
+    }
+    size_t size = 0;
+    r = nvrtcGetCUBINSize(prog, &size);
+    if(r != NVRTC_SUCCESS || size == 0)
+    {
+        *log += "\nnvrtcGetCUBINSize failed";
+        nvrtcDestroyProgram(&prog);
+        return false;
+    }
+    cubin->resize(size);
+    nvrtcGetCUBIN(prog, cubin->data());
+    nvrtcDestroyProgram(&prog);
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// cubin (ELF64) symbol reader
+// ---------------------------------------------------------------------------
+namespace {
+struct Elf64Ehdr
+{
+    unsigned char ident[16];
+    uint16_t type, machine;
+    uint32_t version;
+    uint64_t entry, phoff, shoff;
+    uint32_t flags;
+    uint16_t ehsize, phentsize, phnum, shentsize, shnum, shstrndx;
+};
+struct Elf64Shdr
+{
+    uint32_t name, type;
+    uint64_t flags, addr, offset, size;
+    uint32_t link, info;
+    uint64_t addralign, entsize;
+};
+struct Elf64Sym
+{
+    uint32_t name;
+    unsigned char info, other;
+    uint16_t shndx;
+    uint64_t value, size;
+};
+} // namespace
+
+bool cubin_symbol(const std::vector<char>& cubin, const std::string& symbol,
+                  const unsigned char** bytes, size_t* size)
+{
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(cubin.data());
+    const size_t len = cubin.size();
+    if(len < sizeof(Elf64Ehdr) || memcmp(base, "\177ELF", 4) != 0 || base[4] != 2)
+        return false;
+    Elf64Ehdr eh;
+    memcpy(&eh, base, sizeof(eh));
+    if(eh.shoff == 0 || eh.shentsize != sizeof(Elf64Shdr) || eh.shoff + (uint64_t)eh.shnum*sizeof(Elf64Shdr) > len)
+        return false;
+    std::vector<Elf64Shdr> sh(eh.shnum);
+    memcpy(sh.data(), base + eh.shoff, eh.shnum*sizeof(Elf64Shdr));
+    for(const Elf64Shdr& st : sh)
+    {
+        if(st.type != 2 /* SHT_SYMTAB */ || st.link >= sh.size() || st.entsize != sizeof(Elf64Sym))
+            continue;
+        const Elf64Shdr& str = sh[st.link];
+        if(st.offset + st.size > len || str.offset + str.size > len)
+            return false;
+        const size_t nsym = st.size/sizeof(Elf64Sym);
+        for(size_t i = 0; i < nsym; ++i)
+        {
+            Elf64Sym sym;
+            memcpy(&sym, base + st.offset + i*sizeof(Elf64Sym), sizeof(sym));
+            if(sym.name >= str.size)
+                continue;
+            const char* nm = reinterpret_cast<const char*>(base + str.offset + sym.name);
+            if(symbol != nm)
+                continue;
+            if(sym.shndx == 0 || sym.shndx >= sh.size())
+                return false;
+            const Elf64Shdr& sec = sh[sym.shndx];
+            if(sec.type == 8 /* SHT_NOBITS */ || sym.value + sym.size > sec.size || sec.offset + sec.size > len)
+                return false;
+            *bytes = base + sec.offset + sym.value;
+            *size = sym.size;
+            return true;
+        }
+    }
+    return false;
+}
+
+} // namespace lcu
+
+// ---------------------------------------------------------------------------
+// object cache of a context
+// ---------------------------------------------------------------------------
+std::vector<lcu::Header> lcu_ctx::headers() const
+{
+    return { { "shim.cuh", shim }, { "object.cuh", object_hdr } };
+}
+
+// The reference builds with "-cl-denorms-are-zero -cl-fast-relaxed-math"
+// (src/lensed.c:744-748).  Default here: IEEE division / square root and no
+// FMA contraction, so that object code rounds like the CPU oracle; fast =
+// contraction allowed.  Denormals are flushed either way.
+std::vector<std::string> lcu_ctx::build_options(bool fast) const
+{
+    std::vector<std::string> o = {
+        "--gpu-architecture=sm_100a",
+        "--std=c++17",
+        "--device-as-default-execution-space",
+        "--generate-line-info",
+        "--ftz=true",
+        "--prec-div=true",
+        "--prec-sqrt=true",
+        "-diag-suppress=177,550",
+    };
+    o.push_back(fast ? "--fmad=true" : "--fmad=false");
+    const char* extra = getenv("LCU_NVRTC_FLAGS");
+    if(extra && *extra)
+    {
+        std::istringstream ss(extra);
+        std::string tok;
+        while(ss >> tok)
+            o.push_back(tok);
+    }
+    return o;
+}
+
+const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)
+{
+    using namespace lcu;
+    auto it = objects.find(name);
+    if(it != objects.end())
+        return &it->second;
+
+    if(name.empty() || name.find('/') != std::string::npos)
+    {
+        set_error("invalid object name \"%s\"", name.c_str());
+        return nullptr;
+    }
+
+    bool ok = false;
+    const std::string path = objects_dir + "/" + name + ".cl";
+    const std::string text = read_text_file(path, &ok);
+    if(!ok)
+    {
+        // same wording as the reference, src/kernel.c:757-759
+        set_error("could not load object \"%s\" (file not found: %s)", name.c_str(), path.c_str());
+        return nullptr;
+    }
+
+    ObjectInfo info;
+    info.name = name;
+    info.ident = make_ident(name);
+    info.wrapped = wrap_object(name, info.ident, text);
+
+    // the reference builds object_program() with all image options zero
+    // (src/input/objects.c:89-91); so do we
+    std::string src;
+    src += "#define IMAGE_SIZE 0\n#define IMAGE_WIDTH 0\n#define IMAGE_HEIGHT 0\n"
+           "#define PSF 0\n#define PSF_WIDTH 0\n#define PSF_HEIGHT 0\n#define QUAD_POINTS 0\n";
+    src += "#include \"shim.cuh\"\n#include \"object.cuh\"\n";
+    src += info.wrapped;
+
+    std::vector<char> cubin;
+    std::string log;
+    if(!compile_cubin(src, headers(), build_options(false), &cubin, &log))
+    {
+        set_error("object %s: failed to build program\n%s", name.c_str(), log.c_str());
+        return nullptr;
+    }
+
+    const unsigned char* bytes = nullptr;
+    size_t size = 0;
+    if(!cubin_symbol(cubin, "lcu_meta_" + info.ident, &bytes, &size) || size != 3*sizeof(uint32_t))
+    {
+        set_error("object %s: compiled module has no metadata", name.c_str());
+        return nullptr;
+    }
+    uint32_t meta[3];
+    memcpy(meta, bytes, sizeof(meta));
+    info.type = (int)meta[0];
+    info.bytes = meta[1];
+    // size in 4-byte words, rounding up: src/input/objects.c:139
+    info.words = info.bytes/4 + (info.bytes%4 ? 1 : 0);
+    if(info.type != LCU_LENS && info.type != LCU_SOURCE && info.type != LCU_FOREGROUND)
+    {
+        // src/input/objects.c:147-148
+        set_error("object %s: invalid type (should be LENS, SOURCE or FOREGROUND)", name.c_str());
+        return nullptr;
+    }
+    const size_t npar = meta[2];
+    if(npar > 0)
+    {
+        if(!cubin_symbol(cubin, "lcu_parlst_" + info.ident, &bytes, &size) || size != npar*sizeof(lcu_param))
+        {
+            set_error("object %s: compiled module has no parameter list", name.c_str());
+            return nullptr;
+        }
+        info.params.resize(npar);
+        memcpy(info.params.data(), bytes, size);
+        for(lcu_param& p : info.params)
+            p.name[15] = '\0';
+    }
+
+    // the entry point the type calls for must exist (checked by a second,
+    // cheap look at the text: the compile above would not notice)
+    const char* fn = info.type == LCU_LENS ? "deflection" : info.type == LCU_SOURCE ? "brightness" : "foreground";
+    if(text.find(fn) == std::string::npos || text.find("set") == std::string::npos)
+    {
+        set_error("object %s: missing %s() or set() function", name.c_str(), fn);
+        return nullptr;
+    }
+
+    auto res = objects.emplace(name, std::move(info));
+    return &res.first->second;
+}

@@ -1,0 +1,952 @@
+// lcu_runtime.cpp -- contexts, models, launches: the C ABI of include/lensed_cuda.h.
+//
+// Absorbs the raw OpenCL call sites of the reference: device/context set-up
+// (src/opencl.c:132-241), program build, buffers, kernel arguments and work
+// sizes (src/lensed.c:644-1112), the per-evaluation enqueue sequence and
+// result read-back (src/nested.c:63-115), the dumper's re-render
+// (src/nested.c:178-214) and the profiler (src/profile.c).
+//
+// Device code is compiled per model by NVRTC (lcu_program.cpp) and loaded
+// through the driver API, whose entry points are resolved at run time with
+// cudaGetDriverEntryPoint so that this library has no link-time dependency
+// on libcuda and loads on machines without a GPU (compile-only contexts).
+
+#include "lcu_internal.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+using namespace lcu;
+
+extern "C" int lcu_bench_ffma(int sm_count, double* tflops);     // lcu_bench.cu
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+// ---- driver API, resolved lazily ---------------------------------------------
+struct Driver
+{
+    bool ready = false;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+} drv;
+
+template<typename F>
+bool resolve(const char* name, F* fn)
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+    {
+        set_error("CUDA driver entry point %s not available", name);
+        return false;
+    }
+    *fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+bool init_driver()
+{
+    if(drv.ready)
+        return true;
+    if(!resolve("cuModuleLoadData", &drv.ModuleLoadData) || !resolve("cuModuleUnload", &drv.ModuleUnload)
+       || !resolve("cuModuleGetFunction", &drv.ModuleGetFunction)
+       || !resolve("cuModuleGetGlobal", &drv.ModuleGetGlobal)
+       || !resolve("cuLaunchKernel", &drv.LaunchKernel) || !resolve("cuGetErrorString", &drv.GetErrorString))
+        return false;
+    drv.ready = true;
+    return true;
+}
+
+const char* cu_str(CUresult r)
+{
+    const char* s = nullptr;
+    if(drv.GetErrorString && drv.GetErrorString(r, &s) == CUDA_SUCCESS && s)
+        return s;
+    return "unknown driver error";
+}
+
+#define RT_CHECK(expr) \
+    do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) { \
+        set_error("%s: %s", #expr, cudaGetErrorString(e_)); return LCU_E_CUDA; } } while(0)
+
+#define DRV_CHECK(expr) \
+    do { CUresult r_ = (expr); if(r_ != CUDA_SUCCESS) { \
+        set_error("%s: %s", #expr, cu_str(r_)); return LCU_E_CUDA; } } while(0)
+
+std::string library_dir()
+{
+    Dl_info info;
+    if(dladdr(reinterpret_cast<void*>(&library_dir), &info) && info.dli_fname)
+    {
+        std::string p = info.dli_fname;
+        const size_t s = p.rfind('/');
+        return s == std::string::npos ? std::string(".") : p.substr(0, s);
+    }
+    return ".";
+}
+
+size_t div_up(size_t a, size_t b) { return (a + b - 1)/b; }
+
+// device-side argument blocks: must match kernel/lensed.cu
+struct RenderArgs
+{
+    float pcs[4];
+    long long k0, nk;
+    const uint32_t* objs;
+    float* value;
+    float* error;
+    const float* image;
+    const float* weight;
+    float* chimap;
+    double* partial;
+    int ngroups;
+    int mode;
+};
+
+struct ConvolveArgs
+{
+    const float* raw;
+    float* model;
+    const float* image;
+    const float* weight;
+    float* chimap;
+    double* partial;
+    int row0, row1;
+    int ngroups;
+    int gpr;
+    int mode;
+};
+
+enum { OUT_VALUE = 1, OUT_ERROR = 2, OUT_CHI2 = 4, OUT_CHIMAP = 8 };
+
+} // namespace
+
+struct lcu_model
+{
+    lcu_ctx* ctx = nullptr;
+    std::vector<ModelObject> objs;
+    size_t npars = 0, words = 0;
+    size_t width = 0, height = 0, size = 0;
+    float pcs[4] = { 1, 1, 1, 1 };
+    size_t nq = 0;
+    bool has_psf = false;
+    size_t psfw = 0, psfh = 0;
+    unsigned flags = 0;
+    bool obj_const = true;
+    size_t maxb = 1;
+    size_t row0 = 0, row1 = 0;
+    std::string source, log;
+    std::vector<char> cubin;
+
+    // device state
+    CUmodule mod = nullptr;
+    CUfunction f_set = nullptr, f_render[4] = { nullptr, nullptr, nullptr, nullptr }, f_conv = nullptr, f_reduce = nullptr;
+    CUdeviceptr c_objs = 0;
+    cudaStream_t stream = nullptr;
+    float *d_image = nullptr, *d_weight = nullptr;
+    uint32_t* d_objs = nullptr;         // [maxb][words]
+    float* d_raw = nullptr;             // [maxb][size], PSF models only
+    double* d_partial = nullptr;        // [maxb][max groups]
+    size_t partial_cap = 0;
+    // staging for the host entry points
+    float *d_params = nullptr, *h_params = nullptr;
+    double *d_lnew = nullptr, *h_lnew = nullptr;
+    size_t stage_cap = 0;
+    // dumper buffers (one point), allocated on first lcu_render
+    float *d_value1 = nullptr, *d_error1 = nullptr, *d_model1 = nullptr, *d_chi1 = nullptr;
+    // profiling
+    bool profile = false;
+    lcu_profile prof = {};
+    cudaEvent_t ev[7] = {};
+};
+
+namespace {
+
+int launch(lcu_model* m, CUfunction f, dim3 grid, dim3 block, void** args, cudaStream_t stream)
+{
+    DRV_CHECK(drv.LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0,
+                               reinterpret_cast<CUstream>(stream), args, nullptr));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    (void)m;
+    return LCU_OK;
+}
+
+// rows that have to be rendered so that rows [row0, row1) can be convolved:
+// the PSF window of kernel/lensed.cl:73-76,97 spans rows gj - Ph/2 ... gj - Ph/2 + Ph - 1
+void render_rows(const lcu_model* m, size_t* r0, size_t* r1)
+{
+    if(!m->has_psf)
+    {
+        *r0 = m->row0;
+        *r1 = m->row1;
+        return;
+    }
+    const long long lo = (long long)m->row0 - (long long)(m->psfh/2);
+    const long long hi = (long long)m->row1 - 1 - (long long)(m->psfh/2) + (long long)m->psfh;   // exclusive
+    *r0 = (size_t)std::max<long long>(lo, 0);
+    *r1 = (size_t)std::min<long long>(hi, (long long)m->height);
+}
+
+size_t group_count(const lcu_model* m)
+{
+    if(m->has_psf)
+        return (m->row1 - m->row0)*div_up(m->width, 32);
+    size_t r0, r1;
+    render_rows(m, &r0, &r1);
+    return div_up((r1 - r0)*m->width, 32);
+}
+
+int ensure_partial(lcu_model* m)
+{
+    const size_t need = m->maxb*group_count(m);
+    if(need <= m->partial_cap)
+        return LCU_OK;
+    if(m->d_partial)
+        cudaFree(m->d_partial);
+    m->d_partial = nullptr;
+    RT_CHECK(cudaMalloc(&m->d_partial, need*sizeof(double)));
+    m->partial_cap = need;
+    return LCU_OK;
+}
+
+int ensure_stage(lcu_model* m, size_t nbatch)
+{
+    if(nbatch <= m->stage_cap)
+        return LCU_OK;
+    if(m->d_params) cudaFree(m->d_params);
+    if(m->d_lnew) cudaFree(m->d_lnew);
+    if(m->h_params) cudaFreeHost(m->h_params);
+    if(m->h_lnew) cudaFreeHost(m->h_lnew);
+    m->d_params = nullptr; m->d_lnew = nullptr; m->h_params = nullptr; m->h_lnew = nullptr;
+    m->stage_cap = 0;
+    const size_t cap = std::max<size_t>(nbatch, 64);
+    RT_CHECK(cudaMalloc(&m->d_params, cap*std::max<size_t>(m->npars, 1)*sizeof(float)));
+    RT_CHECK(cudaMalloc(&m->d_lnew, cap*sizeof(double)));
+    RT_CHECK(cudaMallocHost(&m->h_params, cap*std::max<size_t>(m->npars, 1)*sizeof(float)));
+    RT_CHECK(cudaMallocHost(&m->h_lnew, cap*sizeof(double)));
+    m->stage_cap = cap;
+    return LCU_OK;
+}
+
+// how many warps share one 32-pixel group's quadrature points: enough to put
+// ~1024 threads on every SM even for small images / batches
+int pick_split(const lcu_model* m, size_t npix, size_t nb)
+{
+    const char* force = getenv("LCU_SPLIT");
+    if(force && *force)
+    {
+        const int s = atoi(force);
+        if(s == 1 || s == 2 || s == 4 || s == 8)
+            return s;
+    }
+    const size_t target = (size_t)std::max(m->ctx->sm_count, 1)*1024;
+    int s = 1;
+    while(s < 8 && npix*nb*(size_t)s < target)
+        s *= 2;
+    return s;
+}
+
+// enqueue set_params -> render -> (convolve) for `nb` points whose
+// parameters start at d_params; per-point outputs are optional
+int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t st,
+                   float* value, float* error, float* model, float* chimap, bool want_chi2,
+                   cudaEvent_t* ev)
+{
+    // set_params, src/nested.c:77
+    {
+        int B = (int)nb;
+        void* args[] = { &B, (void*)&d_params, &m->d_objs };
+        int rc = launch(m, m->f_set, dim3((unsigned)div_up(nb, 64)), dim3(64), args, st);
+        if(rc) return rc;
+        if(m->obj_const)
+            RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m->c_objs), m->d_objs,
+                                     nb*m->words*sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    if(ev) cudaEventRecord(ev[2], st);
+
+    size_t r0, r1;
+    render_rows(m, &r0, &r1);
+    const size_t nk = (r1 - r0)*m->width;
+    const int ngroups = (int)group_count(m);
+
+    // render, src/nested.c:84
+    {
+        RenderArgs a;
+        memcpy(a.pcs, m->pcs, sizeof(a.pcs));
+        a.k0 = (long long)(r0*m->width);
+        a.nk = (long long)nk;
+        a.objs = m->d_objs;
+        a.value = m->has_psf ? (value ? value : m->d_raw) : value;
+        a.error = error;
+        a.image = m->d_image;
+        a.weight = m->d_weight;
+        a.chimap = m->has_psf ? nullptr : chimap;
+        a.partial = m->d_partial;
+        a.ngroups = ngroups;
+        a.mode = 0;
+        if(a.value) a.mode |= OUT_VALUE;
+        if(a.error) a.mode |= OUT_ERROR;
+        if(!m->has_psf)
+        {
+            if(want_chi2) a.mode |= OUT_CHI2;
+            if(a.chimap) a.mode |= OUT_CHIMAP;
+        }
+        const int split = pick_split(m, nk, nb);
+        const int idx = split == 1 ? 0 : split == 2 ? 1 : split == 4 ? 2 : 3;
+        const size_t ppb = 256/split;
+        void* args[] = { &a };
+        int rc = launch(m, m->f_render[idx], dim3((unsigned)div_up(nk, ppb), (unsigned)nb), dim3(256), args, st);
+        if(rc) return rc;
+    }
+    if(ev) cudaEventRecord(ev[3], st);
+
+    // convolve + loglike, src/nested.c:89-97
+    if(m->has_psf)
+    {
+        ConvolveArgs c;
+        c.raw = value ? value : m->d_raw;
+        c.model = model;
+        c.image = m->d_image;
+        c.weight = m->d_weight;
+        c.chimap = chimap;
+        c.partial = m->d_partial;
+        c.row0 = (int)m->row0;
+        c.row1 = (int)m->row1;
+        c.ngroups = ngroups;
+        c.gpr = (int)div_up(m->width, 32);
+        c.mode = 0;
+        if(model) c.mode |= OUT_VALUE;
+        if(chimap) c.mode |= OUT_CHIMAP;
+        if(want_chi2) c.mode |= OUT_CHI2;
+        void* args[] = { &c };
+        int rc = launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 32), (unsigned)div_up(m->row1 - m->row0, 32), (unsigned)nb),
+                        dim3(256), args, st);
+        if(rc) return rc;
+    }
+    if(ev) cudaEventRecord(ev[4], st);
+    return LCU_OK;
+}
+
+int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_lnew, cudaStream_t st, cudaEvent_t* ev)
+{
+    int rc = ensure_partial(m);
+    if(rc) return rc;
+    const int ngroups = (int)group_count(m);
+    for(size_t b0 = 0; b0 < nbatch; b0 += m->maxb)
+    {
+        const size_t nb = std::min(m->maxb, nbatch - b0);
+        rc = enqueue_points(m, nb, d_params + b0*m->npars, st, nullptr, nullptr, nullptr, nullptr, true,
+                            (ev && b0 == 0) ? ev : nullptr);
+        if(rc) return rc;
+        // host sum of src/nested.c:106-115, on the device
+        int ng = ngroups;
+        double scale = -0.5;
+        double* out = d_lnew + b0;
+        void* args[] = { &ng, &m->d_partial, &scale, &out };
+        rc = launch(m, m->f_reduce, dim3((unsigned)nb), dim3(256), args, st);
+        if(rc) return rc;
+    }
+    if(ev) cudaEventRecord(ev[5], st);
+    return LCU_OK;
+}
+
+void destroy_device_state(lcu_model* m)
+{
+    if(m->ctx && m->ctx->device >= 0)
+        cudaSetDevice(m->ctx->device);
+    for(cudaEvent_t& e : m->ev)
+        if(e) { cudaEventDestroy(e); e = nullptr; }
+    void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_params, m->d_lnew,
+                     m->d_value1, m->d_error1, m->d_model1, m->d_chi1 };
+    for(void* p : bufs)
+        if(p) cudaFree(p);
+    if(m->h_params) cudaFreeHost(m->h_params);
+    if(m->h_lnew) cudaFreeHost(m->h_lnew);
+    if(m->mod && drv.ModuleUnload) drv.ModuleUnload(m->mod);
+    if(m->stream) cudaStreamDestroy(m->stream);
+}
+
+} // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int lcu_version(void) { return LCU_VERSION; }
+
+const char* lcu_last_error(void) { return get_error(); }
+
+unsigned long long lcu_launch_count(void) { return g_launches.load(); }
+
+int lcu_create(int device, const char* kernel_dir, const char* objects_dir, lcu_ctx** out)
+{
+    if(!out)
+    {
+        set_error("lcu_create: null output");
+        return LCU_E_ARG;
+    }
+    *out = nullptr;
+    lcu_ctx* ctx = new lcu_ctx;
+    const std::string base = library_dir();
+    ctx->kernel_dir = kernel_dir ? kernel_dir : base + "/kernel";
+    ctx->objects_dir = objects_dir ? objects_dir : base + "/objects";
+
+    struct { const char* file; std::string* dst; } files[] = {
+        { "shim.cuh", &ctx->shim }, { "object.cuh", &ctx->object_hdr }, { "lensed.cu", &ctx->kernels } };
+    for(auto& f : files)
+    {
+        bool ok = false;
+        *f.dst = read_text_file(ctx->kernel_dir + "/" + f.file, &ok);
+        if(!ok)
+        {
+            // src/kernel.c:680-683
+            set_error("could not load kernel \"%s\" (file not found: %s/%s)", f.file, ctx->kernel_dir.c_str(), f.file);
+            delete ctx;
+            return LCU_E_IO;
+        }
+    }
+
+    ctx->device = device;
+    if(device >= 0)
+    {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if(e != cudaSuccess || device >= count)
+        {
+            set_error("CUDA device %d not available (%s, %d devices)", device,
+                      e != cudaSuccess ? cudaGetErrorString(e) : "out of range", count);
+            delete ctx;
+            return LCU_E_NODEVICE;
+        }
+        if(cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess)
+        {
+            set_error("could not initialise CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+            delete ctx;
+            return LCU_E_CUDA;
+        }
+        cudaDeviceProp prop;
+        if(cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+        {
+            ctx->sm_count = prop.multiProcessorCount;
+            if(prop.major != 10)
+            {
+                set_error("device %d is compute capability %d.%d; this library is built for sm_100a only",
+                          device, prop.major, prop.minor);
+                delete ctx;
+                return LCU_E_NODEVICE;
+            }
+        }
+        if(!init_driver())
+        {
+            delete ctx;
+            return LCU_E_CUDA;
+        }
+    }
+    *out = ctx;
+    return LCU_OK;
+}
+
+void lcu_destroy(lcu_ctx* ctx) { delete ctx; }
+
+int lcu_object_info(lcu_ctx* ctx, const char* name, int* type, size_t* words, size_t* npar,
+                    lcu_param* params, size_t cap)
+{
+    if(!ctx || !name)
+    {
+        set_error("lcu_object_info: null argument");
+        return LCU_E_ARG;
+    }
+    const ObjectInfo* info = ctx->object(name);
+    if(!info)
+    {
+        const std::string msg = get_error();
+        if(msg.find("could not load") != std::string::npos) return LCU_E_IO;
+        if(msg.find("failed to build") != std::string::npos) return LCU_E_COMPILE;
+        return LCU_E_OBJECT;
+    }
+    if(type) *type = info->type;
+    if(words) *words = info->words;
+    if(npar) *npar = info->params.size();
+    if(params)
+        for(size_t i = 0; i < info->params.size() && i < cap; ++i)
+            params[i] = info->params[i];
+    return LCU_OK;
+}
+
+int lcu_quad_rule_count(void) { return quad_rule_count(); }
+const char* lcu_quad_rule_name(int i) { return quad_rule_name(i); }
+const char* lcu_quad_rule_info(int i) { return quad_rule_info(i); }
+int lcu_quad_rule(const char* rule, double sx, double sy, float* qq, float* ww) { return quad_rule(rule, sx, sy, qq, ww); }
+
+int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, const lcu_model_desc* desc, lcu_model** out)
+{
+    if(!ctx || !desc || !out || (nobjs && !specs))
+    {
+        set_error("lcu_model_create: null argument");
+        return LCU_E_ARG;
+    }
+    *out = nullptr;
+    if(desc->width == 0 || desc->height == 0 || desc->nq == 0 || !desc->qq || !desc->ww)
+    {
+        set_error("lcu_model_create: image size and quadrature rule are required");
+        return LCU_E_ARG;
+    }
+    if(desc->width*desc->height > (size_t)1 << 30)
+    {
+        set_error("lcu_model_create: image too large");
+        return LCU_E_ARG;
+    }
+    if(ctx->device >= 0 && (!desc->image || !desc->weight))
+    {
+        set_error("lcu_model_create: image and weight are required");
+        return LCU_E_ARG;
+    }
+    if(desc->psf && (desc->psf_width == 0 || desc->psf_height == 0))
+    {
+        set_error("lcu_model_create: PSF given without size");
+        return LCU_E_ARG;
+    }
+
+    lcu_model* m = new lcu_model;
+    m->ctx = ctx;
+
+    // object list, offsets: src/lensed.c:826-828 (data words), src/kernel.c:632-633 (params)
+    size_t d = 0, p = 0;
+    int nplanes = 0, typ = 0;
+    for(size_t i = 0; i < nobjs; ++i)
+    {
+        if(!specs[i].name)
+        {
+            set_error("lcu_model_create: object %zu has no name", i);
+            delete m;
+            return LCU_E_ARG;
+        }
+        const ObjectInfo* info = ctx->object(specs[i].name);
+        if(!info)
+        {
+            delete m;
+            const std::string msg = get_error();
+            if(msg.find("could not load") != std::string::npos) return LCU_E_IO;
+            if(msg.find("failed to build") != std::string::npos) return LCU_E_COMPILE;
+            return LCU_E_OBJECT;
+        }
+        // src/input/ini.c:249-260
+        if(info->type != typ && info->type != LCU_FOREGROUND)
+        {
+            if(info->type == LCU_LENS && ++nplanes > 1)
+            {
+                set_error("multiple lensing planes are not supported");
+                delete m;
+                return LCU_E_ARG;
+            }
+            typ = info->type;
+        }
+        ModelObject mo;
+        mo.info = info;
+        mo.d = d;
+        mo.p = p;
+        mo.ipp.assign(info->params.size(), 0);
+        for(size_t j = 0; j < info->params.size(); ++j)
+        {
+            mo.ipp[j] = specs[i].ipp ? (specs[i].ipp[j] != 0) : 0;
+            if(!mo.ipp[j])
+                continue;
+            // src/lensed.c:196-234: only (X, Y) pairs can carry image plane priors
+            const int pt = info->params[j].type;
+            bool good = false;
+            if(pt == LCU_POSITION_X)
+                good = j + 1 < info->params.size() && info->params[j + 1].type == LCU_POSITION_Y
+                       && specs[i].ipp[j + 1];
+            else if(pt == LCU_POSITION_Y)
+                good = j > 0 && info->params[j - 1].type == LCU_POSITION_X && specs[i].ipp[j - 1];
+            if(!good)
+            {
+                set_error("object `%s`: image plane prior requires pair (X,Y) of parameters", specs[i].name);
+                delete m;
+                return LCU_E_ARG;
+            }
+        }
+        m->objs.push_back(mo);
+        // data blocks start on 16-byte boundaries (float4 members); every
+        // object shipped with Lensed already has a multiple of 4 words
+        d += (info->words + 3)/4*4;
+        p += info->params.size();
+    }
+    m->words = std::max<size_t>(d, 4);
+    m->npars = p;
+    m->width = desc->width;
+    m->height = desc->height;
+    m->size = desc->width*desc->height;
+    m->row0 = 0;
+    m->row1 = m->height;
+    memcpy(m->pcs, desc->pcs, sizeof(m->pcs));
+    m->nq = desc->nq;
+    m->has_psf = desc->psf != nullptr;
+    m->psfw = m->has_psf ? desc->psf_width : 0;
+    m->psfh = m->has_psf ? desc->psf_height : 0;
+    m->flags = desc->flags;
+    m->obj_const = !(desc->flags & LCU_OBJ_SHARED);
+
+    // fix coordinate system for the half-pixel offset of even PSFs, src/lensed.c:885-891
+    if(m->has_psf)
+    {
+        if(m->psfw % 2 == 0) m->pcs[0] += 0.5f;
+        if(m->psfh % 2 == 0) m->pcs[1] += 0.5f;
+    }
+
+    // points per launch: object blocks share the 64 KB constant bank with the
+    // quadrature table and the PSF; rendered images of PSF models are staged
+    // in HBM (budget LCU_RAW_BUDGET_MB, default 4096)
+    {
+        const size_t used = m->nq*16 + m->psfw*m->psfh*4 + 2048;
+        size_t maxb = used < 65536 ? (65536 - used)/(m->words*4) : 1;
+        maxb = std::min<size_t>(std::max<size_t>(maxb, 1), 1024);
+        if(m->has_psf)
+        {
+            const char* env = getenv("LCU_RAW_BUDGET_MB");
+            const size_t budget = (env && *env ? (size_t)atoll(env) : 4096) << 20;
+            maxb = std::min(maxb, std::max<size_t>(budget/(m->size*sizeof(float)), 1));
+        }
+        if(desc->max_batch)
+            maxb = std::min(maxb, desc->max_batch);
+        m->maxb = maxb;
+    }
+
+    // program text: main_program(), src/kernel.c:838-879 -- ABI headers,
+    // each distinct object once, compute, set_params, kernels
+    {
+        std::ostringstream s;
+        // kernel_options(), src/kernel.c:881-944
+        s << "#define IMAGE_SIZE " << m->size << "\n"
+          << "#define IMAGE_WIDTH " << m->width << "\n"
+          << "#define IMAGE_HEIGHT " << m->height << "\n"
+          << "#define PSF " << (m->has_psf ? 1 : 0) << "\n"
+          << "#define PSF_WIDTH " << m->psfw << "\n"
+          << "#define PSF_HEIGHT " << m->psfh << "\n"
+          << "#define QUAD_POINTS " << m->nq << "\n"
+          << "#define LCU_WORDS " << m->words << "\n"
+          << "#define LCU_NPARS " << std::max<size_t>(m->npars, 1) << "\n"
+          << "#define LCU_MAXB " << m->maxb << "\n"
+          << "#define LCU_OBJ_CONST " << (m->obj_const ? 1 : 0) << "\n"
+          << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
+        std::vector<const ObjectInfo*> uniq;
+        for(const ModelObject& o : m->objs)
+            if(std::find(uniq.begin(), uniq.end(), o.info) == uniq.end())
+                uniq.push_back(o.info);
+        for(const ObjectInfo* info : uniq)
+            s << info->wrapped;
+        s << "//----------------------------------------------------------------------------\n"
+          << "// compute\n"
+          << "//----------------------------------------------------------------------------\n"
+          << generate_compute(m->objs)
+          << "//----------------------------------------------------------------------------\n"
+          << "// set_params\n"
+          << "//----------------------------------------------------------------------------\n"
+          << generate_set_params(m->objs)
+          << "//----------------------------------------------------------------------------\n"
+          << "// kernel/lensed.cu\n"
+          << "//----------------------------------------------------------------------------\n"
+          << "#line 1 \"kernel/lensed.cu\"\n"
+          << ctx->kernels;
+        m->source = s.str();
+    }
+
+    if(!compile_cubin(m->source, ctx->headers(), ctx->build_options((m->flags & LCU_FAST_MATH) != 0), &m->cubin, &m->log))
+    {
+        set_error("failed to build program\n%s", m->log.c_str());
+        delete m;
+        return LCU_E_COMPILE;
+    }
+
+    if(ctx->device < 0)
+    {
+        *out = m;
+        return LCU_OK;
+    }
+
+    // ---- device set-up ---------------------------------------------------
+#define M_CHECK(expr) do { int rc_ = [&]() -> int { expr; return LCU_OK; }(); \
+        if(rc_) { destroy_device_state(m); delete m; return rc_; } } while(0)
+
+    M_CHECK(RT_CHECK(cudaSetDevice(ctx->device)));
+    M_CHECK(RT_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)));
+    M_CHECK(DRV_CHECK(drv.ModuleLoadData(&m->mod, m->cubin.data())));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_set, m->mod, "lcu_set_params")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[0], m->mod, "lcu_render_s1")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[1], m->mod, "lcu_render_s2")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[2], m->mod, "lcu_render_s4")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[3], m->mod, "lcu_render_s8")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
+    if(m->has_psf)
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv, m->mod, "lcu_convolve")));
+
+    // constant tables: quadrature rule (src/lensed.c:817-823) and PSF (:808)
+    {
+        std::vector<float> quad(4*m->nq);
+        for(size_t n = 0; n < m->nq; ++n)
+        {
+            quad[4*n + 0] = desc->qq[2*n + 0];
+            quad[4*n + 1] = desc->qq[2*n + 1];
+            quad[4*n + 2] = desc->ww[2*n + 0];
+            quad[4*n + 3] = desc->ww[2*n + 1];
+        }
+        CUdeviceptr ptr = 0;
+        size_t bytes = 0;
+        M_CHECK(DRV_CHECK(drv.ModuleGetGlobal(&ptr, &bytes, m->mod, "lcu_quad")));
+        M_CHECK(RT_CHECK(cudaMemcpy(reinterpret_cast<void*>(ptr), quad.data(), quad.size()*sizeof(float), cudaMemcpyHostToDevice)));
+        if(m->has_psf)
+        {
+            M_CHECK(DRV_CHECK(drv.ModuleGetGlobal(&ptr, &bytes, m->mod, "lcu_psf")));
+            M_CHECK(RT_CHECK(cudaMemcpy(reinterpret_cast<void*>(ptr), desc->psf, m->psfw*m->psfh*sizeof(float), cudaMemcpyHostToDevice)));
+        }
+        if(m->obj_const)
+        {
+            M_CHECK(DRV_CHECK(drv.ModuleGetGlobal(&m->c_objs, &bytes, m->mod, "lcu_objs_c")));
+        }
+    }
+
+    // data buffers, src/lensed.c:801-812
+    M_CHECK(RT_CHECK(cudaMalloc(&m->d_image, m->size*sizeof(float))));
+    M_CHECK(RT_CHECK(cudaMalloc(&m->d_weight, m->size*sizeof(float))));
+    M_CHECK(RT_CHECK(cudaMemcpy(m->d_image, desc->image, m->size*sizeof(float), cudaMemcpyHostToDevice)));
+    M_CHECK(RT_CHECK(cudaMemcpy(m->d_weight, desc->weight, m->size*sizeof(float), cudaMemcpyHostToDevice)));
+    M_CHECK(RT_CHECK(cudaMalloc(&m->d_objs, m->maxb*m->words*sizeof(uint32_t))));
+    if(m->has_psf)
+        M_CHECK(RT_CHECK(cudaMalloc(&m->d_raw, m->maxb*m->size*sizeof(float))));
+    for(cudaEvent_t& e : m->ev)
+        M_CHECK(RT_CHECK(cudaEventCreate(&e)));
+    M_CHECK(return ensure_partial(m));
+    M_CHECK(return ensure_stage(m, 64));
+#undef M_CHECK
+
+    *out = m;
+    return LCU_OK;
+}
+
+void lcu_model_destroy(lcu_model* m)
+{
+    if(!m)
+        return;
+    destroy_device_state(m);
+    delete m;
+}
+
+size_t lcu_model_npars(const lcu_model* m) { return m ? m->npars : 0; }
+size_t lcu_model_words(const lcu_model* m) { return m ? m->words : 0; }
+size_t lcu_model_max_batch(const lcu_model* m) { return m ? m->maxb : 0; }
+const char* lcu_model_source(const lcu_model* m) { return m ? m->source.c_str() : nullptr; }
+const char* lcu_model_build_log(const lcu_model* m) { return m ? m->log.c_str() : nullptr; }
+
+size_t lcu_model_cubin(const lcu_model* m, const void** image)
+{
+    if(!m)
+        return 0;
+    if(image)
+        *image = m->cubin.data();
+    return m->cubin.size();
+}
+
+int lcu_model_set_rows(lcu_model* m, size_t row0, size_t row1)
+{
+    if(!m || row0 >= row1 || row1 > m->height)
+    {
+        set_error("lcu_model_set_rows: invalid row range");
+        return LCU_E_ARG;
+    }
+    m->row0 = row0;
+    m->row1 = row1;
+    return LCU_OK;
+}
+
+static int need_device(const lcu_model* m, const char* fn)
+{
+    if(!m)
+    {
+        set_error("%s: null model", fn);
+        return LCU_E_ARG;
+    }
+    if(m->ctx->device < 0)
+    {
+        set_error("%s: compile-only context has no device (there is no CPU fallback)", fn);
+        return LCU_E_NODEVICE;
+    }
+    return LCU_OK;
+}
+
+int lcu_loglike_batch_device(lcu_model* m, size_t nbatch, const float* d_params, double* d_lnew, void* stream)
+{
+    int rc = need_device(m, "lcu_loglike_batch_device");
+    if(rc) return rc;
+    if(nbatch == 0)
+        return LCU_OK;
+    if(!d_params || !d_lnew)
+    {
+        set_error("lcu_loglike_batch_device: null argument");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    return enqueue_batch(m, nbatch, d_params, d_lnew, stream ? static_cast<cudaStream_t>(stream) : m->stream, nullptr);
+}
+
+int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* lnew)
+{
+    int rc = need_device(m, "lcu_loglike_batch");
+    if(rc) return rc;
+    if(nbatch == 0)
+        return LCU_OK;
+    if(!params || !lnew)
+    {
+        set_error("lcu_loglike_batch: null argument");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    rc = ensure_stage(m, nbatch);
+    if(rc) return rc;
+    cudaEvent_t* ev = m->profile ? m->ev : nullptr;
+
+    // parameter upload, src/nested.c:67-74
+    memcpy(m->h_params, params, nbatch*m->npars*sizeof(float));
+    if(ev) cudaEventRecord(ev[0], m->stream);
+    RT_CHECK(cudaMemcpyAsync(m->d_params, m->h_params, nbatch*m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    if(ev) cudaEventRecord(ev[1], m->stream);
+    rc = enqueue_batch(m, nbatch, m->d_params, m->d_lnew, m->stream, ev);
+    if(rc) return rc;
+    // result read-back, src/nested.c:102-115 (8 bytes per point instead of the chi^2 map)
+    RT_CHECK(cudaMemcpyAsync(m->h_lnew, m->d_lnew, nbatch*sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    if(ev) cudaEventRecord(ev[6], m->stream);
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    memcpy(lnew, m->h_lnew, nbatch*sizeof(double));
+
+    if(ev)
+    {
+        float t;
+        m->prof.evaluations += nbatch;
+        if(cudaEventElapsedTime(&t, ev[0], ev[1]) == cudaSuccess) m->prof.upload_ms += t;
+        if(cudaEventElapsedTime(&t, ev[1], ev[2]) == cudaSuccess) m->prof.set_params_ms += t;
+        if(cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) m->prof.render_ms += t;
+        if(cudaEventElapsedTime(&t, ev[3], ev[4]) == cudaSuccess) m->prof.convolve_ms += t;
+        if(cudaEventElapsedTime(&t, ev[4], ev[5]) == cudaSuccess) m->prof.reduce_ms += t;
+        if(cudaEventElapsedTime(&t, ev[5], ev[6]) == cudaSuccess) m->prof.download_ms += t;
+    }
+    return LCU_OK;
+}
+
+int lcu_loglike(lcu_model* m, const float* params, double* lnew)
+{
+    return lcu_loglike_batch(m, 1, params, lnew);
+}
+
+int lcu_render(lcu_model* m, const float* params, float* model_img, float* raw, float* err, float* chi)
+{
+    int rc = need_device(m, "lcu_render");
+    if(rc) return rc;
+    if(!params)
+    {
+        set_error("lcu_render: null parameters");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    rc = ensure_stage(m, 1);
+    if(rc) return rc;
+    rc = ensure_partial(m);
+    if(rc) return rc;
+    const size_t bytes = m->size*sizeof(float);
+    float** bufs[] = { &m->d_value1, &m->d_error1, &m->d_model1, &m->d_chi1 };
+    for(float** b : bufs)
+        if(!*b)
+        {
+            RT_CHECK(cudaMalloc(b, bytes));
+            RT_CHECK(cudaMemsetAsync(*b, 0, bytes, m->stream));
+        }
+    memcpy(m->h_params, params, m->npars*sizeof(float));
+    RT_CHECK(cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    rc = enqueue_points(m, 1, m->d_params, m->stream, m->d_value1, m->d_error1,
+                        m->has_psf ? m->d_model1 : nullptr, m->d_chi1, false, nullptr);
+    if(rc) return rc;
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    if(raw) RT_CHECK(cudaMemcpy(raw, m->d_value1, bytes, cudaMemcpyDeviceToHost));
+    if(err) RT_CHECK(cudaMemcpy(err, m->d_error1, bytes, cudaMemcpyDeviceToHost));
+    if(model_img) RT_CHECK(cudaMemcpy(model_img, m->has_psf ? m->d_model1 : m->d_value1, bytes, cudaMemcpyDeviceToHost));
+    if(chi) RT_CHECK(cudaMemcpy(chi, m->d_chi1, bytes, cudaMemcpyDeviceToHost));
+    return LCU_OK;
+}
+
+int lcu_set_params(lcu_model* m, const float* params, uint32_t* block)
+{
+    int rc = need_device(m, "lcu_set_params");
+    if(rc) return rc;
+    if(!params || !block)
+    {
+        set_error("lcu_set_params: null argument");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    rc = ensure_stage(m, 1);
+    if(rc) return rc;
+    memcpy(m->h_params, params, m->npars*sizeof(float));
+    RT_CHECK(cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    int B = 1;
+    void* args[] = { &B, &m->d_params, &m->d_objs };
+    rc = launch(m, m->f_set, dim3(1), dim3(64), args, m->stream);
+    if(rc) return rc;
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    RT_CHECK(cudaMemcpy(block, m->d_objs, m->words*sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return LCU_OK;
+}
+
+int lcu_profile_enable(lcu_model* m, int on)
+{
+    if(!m) return LCU_E_ARG;
+    m->profile = on != 0;
+    if(on)
+        m->prof = lcu_profile{};
+    return LCU_OK;
+}
+
+int lcu_profile_get(const lcu_model* m, lcu_profile* out)
+{
+    if(!m || !out) return LCU_E_ARG;
+    *out = m->prof;
+    return LCU_OK;
+}
+
+int lcu_measure_fp32_peak(lcu_ctx* ctx, double* tflops)
+{
+    if(!ctx || !tflops)
+    {
+        set_error("lcu_measure_fp32_peak: null argument");
+        return LCU_E_ARG;
+    }
+    if(ctx->device < 0)
+    {
+        set_error("lcu_measure_fp32_peak: compile-only context has no device");
+        return LCU_E_NODEVICE;
+    }
+    RT_CHECK(cudaSetDevice(ctx->device));
+    if(lcu_bench_ffma(ctx->sm_count, tflops) != 0)
+    {
+        set_error("FFMA micro-benchmark failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return LCU_E_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return LCU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,352 @@
+// lensed.cu -- hand-written sm_100a kernels of the per-likelihood hot path.
+//
+// Replaces the reference's kernel/lensed.cl (render :9-38, loglike :41-53,
+// convolve :56-103), the generated set_params kernel (src/kernel.c:114-150)
+// and the host-side chi^2 sum of src/nested.c:102-115.  This file is appended
+// by the host (lcu_program.cpp) after the object plugins and the generated
+// lcu_compute() / lcu_set_params_body(), and compiled with NVRTC.  Macros
+// provided by the host: IMAGE_SIZE IMAGE_WIDTH IMAGE_HEIGHT PSF PSF_WIDTH
+// PSF_HEIGHT QUAD_POINTS (src/kernel.c:890-896 names), LCU_WORDS (object block
+// size in 4-byte words), LCU_NPARS, LCU_MAXB (parameter points per launch),
+// LCU_OBJ_CONST (object blocks in the constant bank instead of shared memory).
+//
+// Stages, all batched over parameter points (blockIdx.y = point):
+//   lcu_set_params   1 thread / point : params -> object block
+//   lcu_render_s{S}  pixel x sub-pixel quadrature ray shooting; S warps share
+//                    one 32-pixel group's quadrature points (S = 1 for large
+//                    images, 8 for small ones); the quadrature sum is always
+//                    accumulated in ascending point order, so results do not
+//                    depend on S or on the batch size.  Without a PSF the
+//                    chi^2 terms are fused in.
+//   lcu_convolve     PSF convolution (true, flipped, edge-clamped) from a
+//                    shared-memory tile, PSF in the constant bank, fused with
+//                    the masked weighted chi^2.
+//   lcu_reduce       deterministic double-precision sum of the per-32-pixel
+//                    partials -> log-likelihood.
+//
+// Arithmetic that the reference writes as separate operations is kept as
+// separate IEEE operations (__fmul_rn / __fadd_rn never contract), so the
+// images match the CPU oracle to the last bit wherever libm agrees.
+
+#define LCU_OUT_VALUE  1
+#define LCU_OUT_ERROR  2
+#define LCU_OUT_CHI2   4
+#define LCU_OUT_CHIMAP 8
+
+#define LCU_BLOCK 256
+
+// (qx, qy, weight, error weight) per quadrature point, src/quadrature.c:32-43
+__constant__ float4 lcu_quad[QUAD_POINTS];
+
+#if PSF
+__constant__ float lcu_psf[PSF_WIDTH*PSF_HEIGHT];
+#endif
+
+#if LCU_OBJ_CONST
+// object blocks of the points of the current launch; filled by a
+// device-to-device copy of lcu_set_params' output between the two kernels
+__constant__ uint4 lcu_objs_c[LCU_MAXB*LCU_WORDS/4];
+#endif
+
+struct lcu_render_args
+{
+    float4 pcs;             // (rx, ry, sx, sy), src/lensed.c:879-891
+    long long k0;           // first pixel of the rendered range
+    long long nk;           // number of pixels in the range
+    const uint* objs;       // [B][LCU_WORDS]
+    float* value;           // [B][IMAGE_SIZE] or null
+    float* error;           // [B][IMAGE_SIZE] or null
+    const float* image;     // [IMAGE_SIZE]
+    const float* weight;    // [IMAGE_SIZE]
+    float* chimap;          // [B][IMAGE_SIZE] or null
+    double* partial;        // [B][ngroups]
+    int ngroups;
+    int mode;
+};
+
+// ---------------------------------------------------------------------------
+// set_params: one thread per parameter point
+// ---------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(64)
+lcu_set_params(int B, const float* __restrict__ params, uint* __restrict__ objs)
+{
+    const int b = blockIdx.x*blockDim.x + threadIdx.x;
+    if(b >= B)
+        return;
+
+    __align__(16) uint blk[LCU_WORDS];
+#pragma unroll
+    for(int i = 0; i < LCU_WORDS; ++i)
+        blk[i] = 0;
+
+    lcu_set_params_body(blk, params + (size_t)b*LCU_NPARS);
+
+    uint4* out = reinterpret_cast<uint4*>(objs + (size_t)b*LCU_WORDS);
+#pragma unroll
+    for(int i = 0; i < LCU_WORDS/4; ++i)
+        out[i] = make_uint4(blk[4*i], blk[4*i+1], blk[4*i+2], blk[4*i+3]);
+}
+
+// ---------------------------------------------------------------------------
+// render
+// ---------------------------------------------------------------------------
+
+// quadrature points staged per chunk when several warps share a pixel group
+#define LCU_CHUNK 32
+
+template<int S>
+__device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
+{
+    constexpr int P = LCU_BLOCK/S;          // pixels per block
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int pg = warp/S;                  // 32-pixel group within the block
+    const int ns = warp%S;                  // which share of the points
+    const int b = blockIdx.y;
+
+    const long long kk = (long long)blockIdx.x*P + pg*32 + lane;
+    const bool live = kk < a.nk;
+    const long long k = a.k0 + (live ? kk : 0);
+
+#if LCU_OBJ_CONST
+    const uint* data = reinterpret_cast<const uint*>(lcu_objs_c) + b*LCU_WORDS;
+#else
+    __shared__ __align__(16) uint sdata[LCU_WORDS];
+    for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+        sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
+    __syncthreads();
+    const uint* data = sdata;
+#endif
+
+    // pixel position, kernel/lensed.cl:24
+    const float px = (float)(k % IMAGE_WIDTH);
+    const float py = (float)(k / IMAGE_WIDTH);
+    const float2 x = float2(__fadd_rn(a.pcs.x, __fmul_rn(a.pcs.z, px)),
+                            __fadd_rn(a.pcs.y, __fmul_rn(a.pcs.w, py)));
+
+    // value and error of quadrature, kernel/lensed.cl:27-32
+    float f0 = 0, f1 = 0;
+
+    if(S == 1)
+    {
+        if(live)
+        {
+#pragma unroll 1
+            for(int n = 0; n < QUAD_POINTS; ++n)
+            {
+                const float4 q = lcu_quad[n];
+                const float c = lcu_compute(data, float2(__fadd_rn(x.x, q.x), __fadd_rn(x.y, q.y)));
+                f0 = __fadd_rn(f0, __fmul_rn(q.z, c));
+                f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
+            }
+        }
+    }
+    else
+    {
+        // S warps evaluate interleaved quadrature points of the same 32
+        // pixels into shared memory; warp ns == 0 then adds them up in
+        // ascending order, exactly as the single-warp loop would
+        __shared__ float sc[P][LCU_CHUNK + 1];
+        const int pl = pg*32 + lane;
+        for(int c0 = 0; c0 < QUAD_POINTS; c0 += LCU_CHUNK)
+        {
+            const int c1 = min(c0 + LCU_CHUNK, QUAD_POINTS);
+#pragma unroll 1
+            for(int n = c0 + ns; n < c1; n += S)
+            {
+                const float4 q = lcu_quad[n];
+                sc[pl][n - c0] = lcu_compute(data, float2(__fadd_rn(x.x, q.x), __fadd_rn(x.y, q.y)));
+            }
+            __syncthreads();
+            if(ns == 0)
+            {
+                for(int n = c0; n < c1; ++n)
+                {
+                    const float4 q = lcu_quad[n];
+                    const float c = sc[pl][n - c0];
+                    f0 = __fadd_rn(f0, __fmul_rn(q.z, c));
+                    f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
+                }
+            }
+            __syncthreads();
+        }
+        if(ns != 0)
+            return;
+    }
+
+    // outputs, kernel/lensed.cl:35-37, and the fused loglike kernel
+    // (kernel/lensed.cl:41-53) when there is no PSF
+    const size_t o = (size_t)b*IMAGE_SIZE + k;
+    float chi = 0;
+    if(live)
+    {
+        if(a.mode & LCU_OUT_VALUE)
+            a.value[o] = f0;
+        if(a.mode & LCU_OUT_ERROR)
+            a.error[o] = f1;
+        if(a.mode & (LCU_OUT_CHI2 | LCU_OUT_CHIMAP))
+        {
+            const float d = __fadd_rn(f0, -a.image[k]);
+            chi = __fmul_rn(__fmul_rn(a.weight[k], d), d);
+            if(a.mode & LCU_OUT_CHIMAP)
+                a.chimap[o] = chi;
+        }
+    }
+    if(a.mode & LCU_OUT_CHI2)
+    {
+        // fixed-shape tree over the 32 pixels of the group, in double
+        double s = chi;
+#pragma unroll
+        for(int off = 16; off > 0; off >>= 1)
+            s += __shfl_down_sync(0xffffffffu, s, off);
+        const long long g = ((long long)blockIdx.x*P + pg*32) >> 5;
+        if(lane == 0 && g < a.ngroups)
+            a.partial[(size_t)b*a.ngroups + g] = s;
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_render_s1(const __grid_constant__ lcu_render_args a) { lcu_render_impl<1>(a); }
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_render_s2(const __grid_constant__ lcu_render_args a) { lcu_render_impl<2>(a); }
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_render_s4(const __grid_constant__ lcu_render_args a) { lcu_render_impl<4>(a); }
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_render_s8(const __grid_constant__ lcu_render_args a) { lcu_render_impl<8>(a); }
+
+// ---------------------------------------------------------------------------
+// convolve + chi^2
+// ---------------------------------------------------------------------------
+#if PSF
+
+#define LCU_CT_W 32     // output tile width  (one warp = one row segment)
+#define LCU_CT_H 32     // output tile height
+#define LCU_CT_R (LCU_CT_H/8)
+#define LCU_CW (LCU_CT_W + PSF_WIDTH - 1)
+#define LCU_CH (LCU_CT_H + PSF_HEIGHT - 1)
+
+struct lcu_convolve_args
+{
+    const float* raw;       // [B][IMAGE_SIZE] rendered images
+    float* model;           // [B][IMAGE_SIZE] convolved images or null
+    const float* image;
+    const float* weight;
+    float* chimap;          // [B][IMAGE_SIZE] or null
+    double* partial;        // [B][ngroups]
+    int row0, row1;         // output rows [row0, row1)
+    int ngroups;
+    int gpr;                // groups per row = ceil(IMAGE_WIDTH/32)
+    int mode;
+};
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_convolve(const __grid_constant__ lcu_convolve_args a)
+{
+    __shared__ float tile[LCU_CH][LCU_CW + 1];
+
+    const int tx = threadIdx.x & 31;
+    const int ty = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int gx0 = blockIdx.x*LCU_CT_W;
+    const int gy0 = a.row0 + blockIdx.y*LCU_CT_H;
+
+    const float* raw = a.raw + (size_t)b*IMAGE_SIZE;
+
+    // cache origin and fill, kernel/lensed.cl:73-83: edge-clamped window
+    const int cx = gx0 - PSF_WIDTH/2;
+    const int cy = gy0 - PSF_HEIGHT/2;
+    for(int i = threadIdx.x; i < LCU_CH*LCU_CW; i += LCU_BLOCK)
+    {
+        const int r = i/LCU_CW, c = i%LCU_CW;
+        const int yy = min(max(cy + r, 0), IMAGE_HEIGHT - 1);
+        const int xx = min(max(cx + c, 0), IMAGE_WIDTH - 1);
+        tile[r][c] = raw[(size_t)yy*IMAGE_WIDTH + xx];
+    }
+    __syncthreads();
+
+    // each thread accumulates LCU_CT_R output pixels (rows ty, ty+8, ...) in
+    // the reference's order: PSF rows outer, columns inner, kernel/lensed.cl:95-97
+    float acc[LCU_CT_R];
+#pragma unroll
+    for(int r = 0; r < LCU_CT_R; ++r)
+        acc[r] = 0;
+
+#pragma unroll 1
+    for(int j = 0; j < PSF_HEIGHT; ++j)
+    {
+#pragma unroll
+        for(int i = 0; i < PSF_WIDTH; ++i)
+        {
+            const float p = lcu_psf[j*PSF_WIDTH + i];
+#pragma unroll
+            for(int r = 0; r < LCU_CT_R; ++r)
+                acc[r] = __fadd_rn(acc[r], __fmul_rn(p, tile[ty + 8*r + PSF_HEIGHT - 1 - j][tx + PSF_WIDTH - 1 - i]));
+        }
+    }
+
+    const int gi = gx0 + tx;
+#pragma unroll
+    for(int r = 0; r < LCU_CT_R; ++r)
+    {
+        const int gj = gy0 + ty + 8*r;
+        const bool live = gi < IMAGE_WIDTH && gj < a.row1;
+        float chi = 0;
+        if(live)
+        {
+            const size_t k = (size_t)gj*IMAGE_WIDTH + gi;
+            const size_t o = (size_t)b*IMAGE_SIZE + k;
+            if(a.mode & LCU_OUT_VALUE)
+                a.model[o] = acc[r];
+            // loglike kernel, kernel/lensed.cl:41-53
+            const float d = __fadd_rn(acc[r], -a.image[k]);
+            chi = __fmul_rn(__fmul_rn(a.weight[k], d), d);
+            if(a.mode & LCU_OUT_CHIMAP)
+                a.chimap[o] = chi;
+        }
+        if(a.mode & LCU_OUT_CHI2)
+        {
+            double s = chi;
+#pragma unroll
+            for(int off = 16; off > 0; off >>= 1)
+                s += __shfl_down_sync(0xffffffffu, s, off);
+            if(tx == 0 && gj < a.row1)
+                a.partial[(size_t)b*a.ngroups + (size_t)(gj - a.row0)*a.gpr + blockIdx.x] = s;
+        }
+    }
+}
+
+#endif // PSF
+
+// ---------------------------------------------------------------------------
+// final reduction: one block per point, fixed summation shape
+// out[b] = scale * sum_g partial[b][g]   (scale = -0.5 gives the log-likelihood
+// of src/nested.c:115; scale = 1 the chi^2 of one row strip)
+// ---------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_reduce(int ngroups, const double* __restrict__ partial, double scale, double* __restrict__ out)
+{
+    __shared__ double sm[LCU_BLOCK/32];
+    const int b = blockIdx.x;
+    const double* p = partial + (size_t)b*ngroups;
+
+    double s = 0;
+    for(int g = threadIdx.x; g < ngroups; g += LCU_BLOCK)
+        s += p[g];
+#pragma unroll
+    for(int off = 16; off > 0; off >>= 1)
+        s += __shfl_down_sync(0xffffffffu, s, off);
+    if((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        double t = 0;
+#pragma unroll
+        for(int w = 0; w < LCU_BLOCK/32; ++w)
+            t += sm[w];
+        out[b] = scale*t;
+    }
+}
