@@ -184,8 +184,8 @@ int lcu_loglike(lcu_model* model, const float* params, double* lnew);
 int lcu_loglike_batch(lcu_model* model, size_t nbatch, const float* params, double* lnew);
 
 /* Same with device-resident params / lnew, enqueued on the given CUDA stream
- * (a cudaStream_t passed as void*; NULL = the model's own stream) without
- * synchronising. */
+ * (a cudaStream_t passed as void*; NULL = the CUDA default stream) without
+ * synchronising.  Must not overlap other calls on the same model. */
 int lcu_loglike_batch_device(lcu_model* model, size_t nbatch, const float* d_params,
                              double* d_lnew, void* stream);
 
@@ -201,14 +201,16 @@ int lcu_render(lcu_model* model, const float* params, float* model_img, float* r
 /* object data block produced by set_params for one point (words 4-byte words) */
 int lcu_set_params(lcu_model* model, const float* params, uint32_t* block);
 
-/* Per-stage device times, replaces --profile (src/profile.c:36-83). */
+/* Per-stage device times (CUDA events on the launching stream), replaces
+ * --profile (src/profile.c:36-83).  Works for the host and the device entry
+ * points; lcu_profile_get waits for the launches recorded so far. */
 typedef struct
 {
     unsigned long long evaluations;
     double upload_ms, set_params_ms, render_ms, convolve_ms, reduce_ms, download_ms;
 } lcu_profile;
 int lcu_profile_enable(lcu_model* model, int on);
-int lcu_profile_get(const lcu_model* model, lcu_profile* out);
+int lcu_profile_get(lcu_model* model, lcu_profile* out);
 
 /* FFMA micro-benchmark on the context's device: measured FP32 peak in
  * TFLOP/s, the denominator of the render roofline. */

@@ -218,7 +218,7 @@ class Model:
         return out
 
     def loglike_batch_device(self, nbatch: int, d_params: int, d_lnew: int, stream: int = 0):
-        """Enqueue on ``stream`` (raw cudaStream_t; 0 = the model's own) with
+        """Enqueue on ``stream`` (raw cudaStream_t; 0 = the CUDA default stream) with
         device-resident ``params[nbatch, npars]`` float32 / ``lnew[nbatch]`` float64."""
         check(lib.lcu_loglike_batch_device(self._h, int(nbatch), C.c_void_p(d_params), C.c_void_p(d_lnew),
                                            C.c_void_p(stream) if stream else None))

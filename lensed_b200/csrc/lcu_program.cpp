@@ -103,6 +103,28 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "    (unsigned int)sizeof(struct data_" << id << "),\n"
       << "    (unsigned int)(sizeof(lcu_parlst_" << id << ")/sizeof(struct param))\n"
       << "};\n\n";
+    // Second copy of the object for the parameter setter (and the ray shots
+    // of image-plane priors): same text, but its math built-ins are evaluated
+    // in double and rounded once (shim.cuh: LCU_ACCURATE_ON).  set_params runs
+    // one thread per parameter point, so this costs nothing measurable and
+    // makes the object block agree with a correctly rounding host libm.
+    s << "namespace lcu_setter {\n"
+      << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
+      << "#define LCU_ACCURATE_ON\n#include \"shim.cuh\"\n"
+      << "#define type const int type_" << id << "\n"
+      << "#define params const struct param parlst_" << id << "[] = \n"
+      << "#define data struct data_" << id << "\n"
+      << "#define deflection deflection_" << id << "\n"
+      << "#define brightness brightness_" << id << "\n"
+      << "#define foreground foreground_" << id << "\n"
+      << "#define set set_" << id << "\n"
+      << "#line 1 \"objects/" << name << ".cl\"\n"
+      << rewrite_literals(text) << "\n"
+      << "#undef type\n#undef params\n#undef data\n#undef deflection\n"
+      << "#undef brightness\n#undef foreground\n#undef set\n"
+      << "#define LCU_ACCURATE_OFF\n#include \"shim.cuh\"\n"
+      << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
+      << "} // namespace lcu_setter\n\n";
     return s.str();
 }
 
@@ -200,13 +222,13 @@ std::string generate_set_params(const std::vector<ModelObject>& objs)
                     trigger2 = l.info->type;
                 }
                 if(l.info->type == LCU_LENS)
-                    s << "    a += deflection_" << l.info->ident << "((struct data_" << l.info->ident
+                    s << "    a += lcu_setter::deflection_" << l.info->ident << "((struct lcu_setter::data_" << l.info->ident
                       << "*)(data + " << l.d << "), x);\n";
             }
             if(trigger2 == LCU_LENS)
                 s << "    x" << DEFLECT << "    a = 0;\n";
         }
-        s << "    set_" << id << "((struct data_" << id << "*)(data + " << o.d << ")";
+        s << "    lcu_setter::set_" << id << "((struct lcu_setter::data_" << id << "*)(data + " << o.d << ")";
         for(size_t j = 0; j < o.info->params.size(); ++j)
         {
             if(o.ipp[j])

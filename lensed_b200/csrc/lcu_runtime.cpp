@@ -170,10 +170,13 @@ struct lcu_model
     size_t stage_cap = 0;
     // dumper buffers (one point), allocated on first lcu_render
     float *d_value1 = nullptr, *d_error1 = nullptr, *d_model1 = nullptr, *d_chi1 = nullptr;
-    // profiling
+    // profiling: one set of stage events per launched chunk, harvested lazily
+    struct EventSet { cudaEvent_t e[5]; size_t nb; };
     bool profile = false;
     lcu_profile prof = {};
-    cudaEvent_t ev[7] = {};
+    std::vector<EventSet> evsets;       // pool
+    size_t evused = 0;                  // sets recorded since the last harvest
+    cudaEvent_t ev_io[4] = {};          // host path: upload begin/end, download begin/end
 };
 
 namespace {
@@ -268,6 +271,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
                    float* value, float* error, float* model, float* chimap, bool want_chi2,
                    cudaEvent_t* ev)
 {
+    if(ev) cudaEventRecord(ev[0], st);
     // set_params, src/nested.c:77
     {
         int B = (int)nb;
@@ -278,7 +282,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
             RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m->c_objs), m->d_objs,
                                      nb*m->words*sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
-    if(ev) cudaEventRecord(ev[2], st);
+    if(ev) cudaEventRecord(ev[1], st);
 
     size_t r0, r1;
     render_rows(m, &r0, &r1);
@@ -314,7 +318,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         int rc = launch(m, m->f_render[idx], dim3((unsigned)div_up(nk, ppb), (unsigned)nb), dim3(256), args, st);
         if(rc) return rc;
     }
-    if(ev) cudaEventRecord(ev[3], st);
+    if(ev) cudaEventRecord(ev[2], st);
 
     // convolve + loglike, src/nested.c:89-97
     if(m->has_psf)
@@ -339,11 +343,48 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
                         dim3(256), args, st);
         if(rc) return rc;
     }
-    if(ev) cudaEventRecord(ev[4], st);
+    if(ev) cudaEventRecord(ev[3], st);
     return LCU_OK;
 }
 
-int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_lnew, cudaStream_t st, cudaEvent_t* ev)
+// stage events of the next chunk (profiling only); the pool grows on demand
+cudaEvent_t* next_event_set(lcu_model* m, size_t nb)
+{
+    if(!m->profile)
+        return nullptr;
+    if(m->evused == m->evsets.size())
+    {
+        lcu_model::EventSet es;
+        es.nb = 0;
+        for(cudaEvent_t& e : es.e)
+            if(cudaEventCreate(&e) != cudaSuccess)
+                return nullptr;
+        m->evsets.push_back(es);
+    }
+    lcu_model::EventSet& es = m->evsets[m->evused++];
+    es.nb = nb;
+    return es.e;
+}
+
+// wait for the recorded chunks and add their stage times to the profile
+void harvest_profile(lcu_model* m)
+{
+    for(size_t i = 0; i < m->evused; ++i)
+    {
+        lcu_model::EventSet& es = m->evsets[i];
+        float t;
+        if(cudaEventSynchronize(es.e[4]) != cudaSuccess)
+            continue;
+        m->prof.evaluations += es.nb;
+        if(cudaEventElapsedTime(&t, es.e[0], es.e[1]) == cudaSuccess) m->prof.set_params_ms += t;
+        if(cudaEventElapsedTime(&t, es.e[1], es.e[2]) == cudaSuccess) m->prof.render_ms += t;
+        if(cudaEventElapsedTime(&t, es.e[2], es.e[3]) == cudaSuccess) m->prof.convolve_ms += t;
+        if(cudaEventElapsedTime(&t, es.e[3], es.e[4]) == cudaSuccess) m->prof.reduce_ms += t;
+    }
+    m->evused = 0;
+}
+
+int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_lnew, cudaStream_t st)
 {
     int rc = ensure_partial(m);
     if(rc) return rc;
@@ -351,8 +392,8 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
     for(size_t b0 = 0; b0 < nbatch; b0 += m->maxb)
     {
         const size_t nb = std::min(m->maxb, nbatch - b0);
-        rc = enqueue_points(m, nb, d_params + b0*m->npars, st, nullptr, nullptr, nullptr, nullptr, true,
-                            (ev && b0 == 0) ? ev : nullptr);
+        cudaEvent_t* ev = next_event_set(m, nb);
+        rc = enqueue_points(m, nb, d_params + b0*m->npars, st, nullptr, nullptr, nullptr, nullptr, true, ev);
         if(rc) return rc;
         // host sum of src/nested.c:106-115, on the device
         int ng = ngroups;
@@ -361,8 +402,8 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
         void* args[] = { &ng, &m->d_partial, &scale, &out };
         rc = launch(m, m->f_reduce, dim3((unsigned)nb), dim3(256), args, st);
         if(rc) return rc;
+        if(ev) cudaEventRecord(ev[4], st);
     }
-    if(ev) cudaEventRecord(ev[5], st);
     return LCU_OK;
 }
 
@@ -370,8 +411,12 @@ void destroy_device_state(lcu_model* m)
 {
     if(m->ctx && m->ctx->device >= 0)
         cudaSetDevice(m->ctx->device);
-    for(cudaEvent_t& e : m->ev)
+    for(cudaEvent_t& e : m->ev_io)
         if(e) { cudaEventDestroy(e); e = nullptr; }
+    for(lcu_model::EventSet& es : m->evsets)
+        for(cudaEvent_t& e : es.e)
+            cudaEventDestroy(e);
+    m->evsets.clear();
     void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_params, m->d_lnew,
                      m->d_value1, m->d_error1, m->d_model1, m->d_chi1 };
     for(void* p : bufs)
@@ -730,7 +775,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(RT_CHECK(cudaMalloc(&m->d_objs, m->maxb*m->words*sizeof(uint32_t))));
     if(m->has_psf)
         M_CHECK(RT_CHECK(cudaMalloc(&m->d_raw, m->maxb*m->size*sizeof(float))));
-    for(cudaEvent_t& e : m->ev)
+    for(cudaEvent_t& e : m->ev_io)
         M_CHECK(RT_CHECK(cudaEventCreate(&e)));
     M_CHECK(return ensure_partial(m));
     M_CHECK(return ensure_stage(m, 64));
@@ -802,7 +847,7 @@ int lcu_loglike_batch_device(lcu_model* m, size_t nbatch, const float* d_params,
         return LCU_E_ARG;
     }
     RT_CHECK(cudaSetDevice(m->ctx->device));
-    return enqueue_batch(m, nbatch, d_params, d_lnew, stream ? static_cast<cudaStream_t>(stream) : m->stream, nullptr);
+    return enqueue_batch(m, nbatch, d_params, d_lnew, static_cast<cudaStream_t>(stream));
 }
 
 int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* lnew)
@@ -819,31 +864,28 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
     RT_CHECK(cudaSetDevice(m->ctx->device));
     rc = ensure_stage(m, nbatch);
     if(rc) return rc;
-    cudaEvent_t* ev = m->profile ? m->ev : nullptr;
+    cudaEvent_t* ev = m->profile ? m->ev_io : nullptr;
 
     // parameter upload, src/nested.c:67-74
     memcpy(m->h_params, params, nbatch*m->npars*sizeof(float));
     if(ev) cudaEventRecord(ev[0], m->stream);
     RT_CHECK(cudaMemcpyAsync(m->d_params, m->h_params, nbatch*m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream));
     if(ev) cudaEventRecord(ev[1], m->stream);
-    rc = enqueue_batch(m, nbatch, m->d_params, m->d_lnew, m->stream, ev);
+    rc = enqueue_batch(m, nbatch, m->d_params, m->d_lnew, m->stream);
     if(rc) return rc;
     // result read-back, src/nested.c:102-115 (8 bytes per point instead of the chi^2 map)
+    if(ev) cudaEventRecord(ev[2], m->stream);
     RT_CHECK(cudaMemcpyAsync(m->h_lnew, m->d_lnew, nbatch*sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-    if(ev) cudaEventRecord(ev[6], m->stream);
+    if(ev) cudaEventRecord(ev[3], m->stream);
     RT_CHECK(cudaStreamSynchronize(m->stream));
     memcpy(lnew, m->h_lnew, nbatch*sizeof(double));
 
     if(ev)
     {
         float t;
-        m->prof.evaluations += nbatch;
         if(cudaEventElapsedTime(&t, ev[0], ev[1]) == cudaSuccess) m->prof.upload_ms += t;
-        if(cudaEventElapsedTime(&t, ev[1], ev[2]) == cudaSuccess) m->prof.set_params_ms += t;
-        if(cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) m->prof.render_ms += t;
-        if(cudaEventElapsedTime(&t, ev[3], ev[4]) == cudaSuccess) m->prof.convolve_ms += t;
-        if(cudaEventElapsedTime(&t, ev[4], ev[5]) == cudaSuccess) m->prof.reduce_ms += t;
-        if(cudaEventElapsedTime(&t, ev[5], ev[6]) == cudaSuccess) m->prof.download_ms += t;
+        if(cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) m->prof.download_ms += t;
+        harvest_profile(m);
     }
     return LCU_OK;
 }
@@ -914,15 +956,22 @@ int lcu_set_params(lcu_model* m, const float* params, uint32_t* block)
 int lcu_profile_enable(lcu_model* m, int on)
 {
     if(!m) return LCU_E_ARG;
+    if(m->profile)
+        harvest_profile(m);
     m->profile = on != 0;
     if(on)
         m->prof = lcu_profile{};
     return LCU_OK;
 }
 
-int lcu_profile_get(const lcu_model* m, lcu_profile* out)
+int lcu_profile_get(lcu_model* m, lcu_profile* out)
 {
     if(!m || !out) return LCU_E_ARG;
+    if(m->ctx->device >= 0)
+    {
+        cudaSetDevice(m->ctx->device);
+        harvest_profile(m);         // waits for the chunks recorded so far
+    }
     *out = m->prof;
     return LCU_OK;
 }

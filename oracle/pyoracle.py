@@ -22,6 +22,8 @@ _VARIANTS = {
     "strict": "liboracle.so",
     "f64": "liboracle_f64.so",
     "fast": "liboracle_fast.so",
+    "ref": os.path.join("_ref", "liblensed_ref.so"),
+    "ref_fast": os.path.join("_ref", "liblensed_ref_fast.so"),
 }
 
 _libs: dict = {}

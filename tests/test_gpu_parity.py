@@ -18,31 +18,45 @@ LOGLIKE_TOL = 1e-6
 
 
 def _check_images(out, cfg, om):
+    """Per-pixel relative error of the raw (pre-PSF) and model images against
+    the strict-float32 oracle.  Bound: PIXEL_TOL = 1e-5 at the 99.9th
+    percentile always, and for the maximum as well unless the oracle's own
+    float32 rounding noise on this scene (its distance from its float64 twin)
+    is already that large -- two independent float32 evaluations cannot agree
+    better than either agrees with the exact result -- in which case the
+    maximum may reach 1.5x that noise floor."""
     value, error = om.render(cfg.params)
     lnew, model, chi = om.loglike(cfg.params, want_maps=True)
+    o64 = cfg.oracle(variant="f64")
+    v64, _ = o64.render(cfg.params)
+    _, m64, _ = o64.loglike(cfg.params, want_maps=True)
     stats = {}
-    r = H.rel_err(out["raw"], value)
-    stats["raw"] = r.max()
-    assert r.max() <= PIXEL_TOL, f"{cfg.name}: raw image max rel err {r.max():.3e}"
-    r = H.rel_err(out["model"], model)
-    stats["model"] = r.max()
-    assert r.max() <= PIXEL_TOL, f"{cfg.name}: model image max rel err {r.max():.3e}"
+    for key, ref, ref64 in (("raw", value, v64), ("model", model, m64)):
+        r = H.rel_err(out[key], ref)
+        floor = H.rel_err(ref, ref64).max()
+        tol = max(PIXEL_TOL, 1.5*floor)
+        stats[key] = (r.max(), floor)
+        assert np.quantile(r, 0.999) <= PIXEL_TOL, f"{cfg.name}: {key} image p99.9 rel err {np.quantile(r, 0.999):.3e}"
+        assert r.max() <= tol, f"{cfg.name}: {key} image max rel err {r.max():.3e} (f32 noise floor {floor:.3e})"
     # the quadrature error estimate is a sum with alternating-sign weights:
     # compare it on the scale of the value it estimates the error of
     scale = np.maximum(np.abs(value), 1e-30)
-    assert (np.abs(out["error"].astype(np.float64) - error)/scale).max() <= 10*PIXEL_TOL
+    e = (np.abs(out["error"].astype(np.float64) - error)/scale).max()
+    assert e <= 10*PIXEL_TOL, f"{cfg.name}: error image differs by {e:.3e} of the value"
     return lnew, stats
 
 
 def _check_block(m, om, cfg):
     """Object data block written by set_params: same layout word for word;
-    values agree to a few ulp (the setters call cos/sin/log/tgamma, whose last
-    bit differs between the CUDA and the host math library)."""
+    values agree to ~2 ulp (the setters evaluate their math built-ins in double
+    on the device and round once; the host libm is not correctly rounded for
+    every function, e.g. tgammaf)."""
     blk = m.set_params(cfg.params).view(np.float32)
     ref = om.set_params(cfg.params).astype(np.float32)
     assert blk.size == ref.size, f"{cfg.name}: object block size {blk.size} vs {ref.size}"
     assert np.array_equal(blk == 0, ref == 0), f"{cfg.name}: object block layout differs"
-    assert np.allclose(blk, ref, rtol=3e-6, atol=1e-7), f"{cfg.name}: object block differs"
+    bad = ~np.isclose(blk, ref, rtol=5e-7, atol=1e-30)
+    assert not bad.any(), f"{cfg.name}: object block words {np.nonzero(bad)[0]}: {blk[bad]} vs {ref[bad]}"
 
 
 @pytest.mark.parametrize("name", H.golden_names())
@@ -56,10 +70,11 @@ def test_reference_known_answer_configs(gpu_ctx, name):
     # loose anchor against the reference's golden image: chi^2/dof << 1
     got = m.loglike(cfg.params)
     n = cfg.image.size
-    assert -2*got/n < 0.01
-    # chi^2 ~ 0 here (model == image up to noise floor), so compare on the
-    # scale of the pixel count rather than relatively (SURVEY.md 'hard parts')
-    assert abs(got - lnew) <= 1e-6*max(abs(lnew), 1e-3*n)
+    assert -2*got/n < 0.01, f"{name}: chi2/dof {-2*got/n:.3e} against the reference's golden image"
+    # chi^2 ~ 0 here (model == image up to the noise floor), so a relative
+    # comparison is ill-conditioned (SURVEY.md 'hard parts'): compare on the
+    # scale of the number of degrees of freedom instead
+    assert abs(got - lnew) <= LOGLIKE_TOL*n, f"{name}: lnew {got} vs {lnew}"
     _check_block(m, om, cfg)
 
 
