@@ -82,6 +82,8 @@ SYMBOLS = {
 
 LCU_FAST_MATH = 1
 LCU_OBJ_SHARED = 2
+LCU_FAST_INTRINSICS = 4
+LCU_FAST_DIVSQRT = 8
 
 
 def _load():

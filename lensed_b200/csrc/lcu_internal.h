@@ -85,5 +85,5 @@ struct lcu_ctx
 
     const lcu::ObjectInfo* object(const std::string& name);     // loads + compiles on first use
     std::vector<lcu::Header> headers() const;
-    std::vector<std::string> build_options(bool fast) const;
+    std::vector<std::string> build_options(unsigned flags) const;
 };

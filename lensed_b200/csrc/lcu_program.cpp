@@ -382,22 +382,27 @@ std::vector<lcu::Header> lcu_ctx::headers() const
 }
 
 // The reference builds with "-cl-denorms-are-zero -cl-fast-relaxed-math"
-// (src/lensed.c:744-748).  Default here: IEEE division / square root and no
-// FMA contraction, so that object code rounds like the CPU oracle; fast =
-// contraction allowed.  Denormals are flushed either way.
-std::vector<std::string> lcu_ctx::build_options(bool fast) const
+// (src/lensed.c:744-748).  Default here: IEEE division / square root, accurate
+// libdevice transcendentals and no FMA contraction, so that object code rounds
+// like the CPU oracle.  Opt-in relaxations (model flags): LCU_FAST_MATH = FMA
+// contraction, LCU_FAST_INTRINSICS = hardware exp2/log2/sin/cos approximations
+// for expf/logf/..., LCU_FAST_DIVSQRT = approximate division and square root.
+// Denormals are flushed either way.
+std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
 {
     std::vector<std::string> o = {
         "--gpu-architecture=sm_100a",
         "--std=c++17",
         "--device-as-default-execution-space",
         "--generate-line-info",
-        "--ftz=true",
-        "--prec-div=true",
-        "--prec-sqrt=true",
         "-diag-suppress=177,550",
     };
-    o.push_back(fast ? "--fmad=true" : "--fmad=false");
+    if(flags & LCU_FAST_INTRINSICS)
+        o.push_back("--use_fast_math");
+    o.push_back("--ftz=true");
+    o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-div=false" : "--prec-div=true");
+    o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-sqrt=false" : "--prec-sqrt=true");
+    o.push_back((flags & LCU_FAST_MATH) ? "--fmad=true" : "--fmad=false");
     const char* extra = getenv("LCU_NVRTC_FLAGS");
     if(extra && *extra)
     {
@@ -447,7 +452,7 @@ const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)
 
     std::vector<char> cubin;
     std::string log;
-    if(!compile_cubin(src, headers(), build_options(false), &cubin, &log))
+    if(!compile_cubin(src, headers(), build_options(0), &cubin, &log))
     {
         set_error("object %s: failed to build program\n%s", name.c_str(), log.c_str());
         return nullptr;

@@ -713,7 +713,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
         m->source = s.str();
     }
 
-    if(!compile_cubin(m->source, ctx->headers(), ctx->build_options((m->flags & LCU_FAST_MATH) != 0), &m->cubin, &m->log))
+    if(!compile_cubin(m->source, ctx->headers(), ctx->build_options(m->flags), &m->cubin, &m->log))
     {
         set_error("failed to build program\n%s", m->log.c_str());
         delete m;
