@@ -127,8 +127,9 @@ typedef struct
                                 default is one IEEE operation per source operation */
 #define LCU_OBJ_SHARED  2u   /* keep object blocks in shared memory instead of
                                 the constant bank */
-#define LCU_FAST_INTRINSICS 4u  /* expf/logf/sinf/cosf/powf -> hardware exp2/log2/sin/cos
-                                   approximations (nvcc --use_fast_math semantics) */
+#define LCU_FAST_INTRINSICS 4u  /* exp/log/pow/sin/cos -> hardware exp2/log2/sin/cos
+                                   approximations in SOURCE and FOREGROUND objects */
+#define LCU_FAST_LENS_INTRINSICS 16u /* the same in LENS objects (less accurate deflections) */
 #define LCU_FAST_DIVSQRT    8u  /* approximate division and square root (2 ulp) */
 
 typedef struct

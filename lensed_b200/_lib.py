@@ -84,6 +84,7 @@ LCU_FAST_MATH = 1
 LCU_OBJ_SHARED = 2
 LCU_FAST_INTRINSICS = 4
 LCU_FAST_DIVSQRT = 8
+LCU_FAST_LENS_INTRINSICS = 16
 
 
 def _load():

@@ -86,6 +86,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "// objects/" << name << ".cl\n"
       << "//----------------------------------------------------------------------------\n"
       << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
+      << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"
       << "#define type const int type_" << id << "\n"
       << "#define params extern \"C\" __device__ const struct param lcu_parlst_" << id << "[] = \n"
       << "#define data struct data_" << id << "\n"
@@ -97,6 +98,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << rewrite_literals(text) << "\n"
       << "#undef type\n#undef params\n#undef data\n#undef deflection\n"
       << "#undef brightness\n#undef foreground\n#undef set\n"
+      << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_OFF\n#include \"shim.cuh\"\n#endif\n"
       << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
       << "extern \"C\" __device__ const unsigned int lcu_meta_" << id << "[3] = {\n"
       << "    (unsigned int)type_" << id << ",\n"
@@ -386,7 +388,10 @@ std::vector<lcu::Header> lcu_ctx::headers() const
 // libdevice transcendentals and no FMA contraction, so that object code rounds
 // like the CPU oracle.  Opt-in relaxations (model flags): LCU_FAST_MATH = FMA
 // contraction, LCU_FAST_INTRINSICS = hardware exp2/log2/sin/cos approximations
-// for expf/logf/..., LCU_FAST_DIVSQRT = approximate division and square root.
+// for exp/log/pow/sin/cos in source and foreground objects (remapped at source
+// level by shim.cuh; measured as accurate as the strict build on Sersic
+// scenes), LCU_FAST_LENS_INTRINSICS = the same in lens objects (costs accuracy
+// in the deflection), LCU_FAST_DIVSQRT = approximate division and square root.
 // Denormals are flushed either way.
 std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
 {
@@ -397,8 +402,8 @@ std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
         "--generate-line-info",
         "-diag-suppress=177,550",
     };
-    if(flags & LCU_FAST_INTRINSICS)
-        o.push_back("--use_fast_math");
+    o.push_back((flags & LCU_FAST_INTRINSICS) ? "-DLCU_INTRINSICS_SOURCE=1" : "-DLCU_INTRINSICS_SOURCE=0");
+    o.push_back((flags & LCU_FAST_LENS_INTRINSICS) ? "-DLCU_INTRINSICS_LENS=1" : "-DLCU_INTRINSICS_LENS=0");
     o.push_back("--ftz=true");
     o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-div=false" : "--prec-div=true");
     o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-sqrt=false" : "--prec-sqrt=true");
@@ -448,7 +453,13 @@ const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)
     src += "#define IMAGE_SIZE 0\n#define IMAGE_WIDTH 0\n#define IMAGE_HEIGHT 0\n"
            "#define PSF 0\n#define PSF_WIDTH 0\n#define PSF_HEIGHT 0\n#define QUAD_POINTS 0\n";
     src += "#include \"shim.cuh\"\n#include \"object.cuh\"\n";
-    src += info.wrapped;
+    {
+        std::string w = info.wrapped;
+        size_t pos;
+        while((pos = w.find("@KIND@")) != std::string::npos)
+            w.replace(pos, 6, "SOURCE");
+        src += w;
+    }
 
     std::vector<char> cubin;
     std::string log;
@@ -471,6 +482,13 @@ const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)
     info.bytes = meta[1];
     // size in 4-byte words, rounding up: src/input/objects.c:139
     info.words = info.bytes/4 + (info.bytes%4 ? 1 : 0);
+    {
+        // which relaxed-math switch governs this object: lenses have their own
+        const std::string kind = info.type == LCU_LENS ? "LENS" : "SOURCE";
+        size_t pos;
+        while((pos = info.wrapped.find("@KIND@")) != std::string::npos)
+            info.wrapped.replace(pos, 6, kind);
+    }
     if(info.type != LCU_LENS && info.type != LCU_SOURCE && info.type != LCU_FOREGROUND)
     {
         // src/input/objects.c:147-148

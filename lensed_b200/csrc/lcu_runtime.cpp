@@ -151,6 +151,7 @@ struct lcu_model
     bool obj_const = true;
     size_t maxb = 1;
     size_t row0 = 0, row1 = 0;
+    size_t conv_tile_h = 32;            // must match LCU_CT_H in kernel/lensed.cu
     std::string source, log;
     std::vector<char> cubin;
 
@@ -339,7 +340,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         if(chimap) c.mode |= OUT_CHIMAP;
         if(want_chi2) c.mode |= OUT_CHI2;
         void* args[] = { &c };
-        int rc = launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 32), (unsigned)div_up(m->row1 - m->row0, 32), (unsigned)nb),
+        int rc = launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 64), (unsigned)div_up(m->row1 - m->row0, m->conv_tile_h), (unsigned)nb),
                         dim3(256), args, st);
         if(rc) return rc;
     }
@@ -648,6 +649,21 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     m->psfh = m->has_psf ? desc->psf_height : 0;
     m->flags = desc->flags;
     m->obj_const = !(desc->flags & LCU_OBJ_SHARED);
+
+    if(m->has_psf)
+    {
+        // convolution tile height: same arithmetic as LCU_CT_H in kernel/lensed.cu
+        const size_t nv = (8 + m->psfw - 1 + 3)/4;
+        const size_t cwmin = 56 + 4*nv;
+        const size_t cw = cwmin + ((12 - cwmin%8)%8);
+        m->conv_tile_h = cw*(32 + m->psfh - 1)*4 <= 48*1024 ? 32 : cw*(16 + m->psfh - 1)*4 <= 48*1024 ? 16 : 8;
+        if(cw*(8 + m->psfh - 1)*4 > 48*1024)
+        {
+            set_error("lcu_model_create: PSF %zu x %zu too large for the convolution tile", m->psfw, m->psfh);
+            delete m;
+            return LCU_E_ARG;
+        }
+    }
 
     // fix coordinate system for the half-pixel offset of even PSFs, src/lensed.c:885-891
     if(m->has_psf)
