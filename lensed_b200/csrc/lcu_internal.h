@@ -81,9 +81,12 @@ struct lcu_ctx
     std::string kernel_dir, objects_dir;
     std::string shim, object_hdr, kernels;      // kernel/*.cuh, lensed.cu text
     std::map<std::string, lcu::ObjectInfo> objects;
+    std::map<std::string, std::vector<char>> cubins;            // compiled programs by options + source text
     int sm_count = 0;
 
     const lcu::ObjectInfo* object(const std::string& name);     // loads + compiles on first use
     std::vector<lcu::Header> headers() const;
     std::vector<std::string> build_options(unsigned flags) const;
+    // NVRTC with an in-process cache: identical program text + options compile once
+    bool compile(const std::string& source, unsigned flags, std::vector<char>* cubin, std::string* log);
 };

@@ -149,6 +149,11 @@ std::string generate_compute(const std::vector<ModelObject>& objs)
       << "    float f = 0;\n";
     int type = 0, trigger = 0;
     bool open = false;
+    // The reference starts every sum from zero ("float2 a = 0; a += ...",
+    // "float f = 0; f += ...").  The first term is assigned instead: 0 + t == t
+    // for every t except t = -0, whose sign no later operation can observe
+    // (y - a, f + ...), and the compiler may not drop the addition itself.
+    bool first_lens = false, first_light = true;
     for(const ModelObject& o : objs)
     {
         const int t = o.info->type;
@@ -166,18 +171,24 @@ std::string generate_compute(const std::vector<ModelObject>& objs)
         {
             if(t == LCU_LENS && !open)
             {
-                s << "    {\n        lcu_float2 a = 0;\n";
+                s << "    {\n        lcu_float2 a;\n";
                 open = true;
+                first_lens = true;
             }
             type = t;
         }
         const char* ind = open ? "        " : "    ";
         if(t == LCU_LENS)
-            s << ind << "a += deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
-        else if(t == LCU_SOURCE)
-            s << ind << "f += brightness_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+        {
+            s << ind << (first_lens ? "a = " : "a += ") << "deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+            first_lens = false;
+        }
         else
-            s << ind << "f += foreground_" << id << "((struct data_" << id << "*)(data + " << o.d << "), x);\n";
+        {
+            s << ind << (first_light ? "f = " : "f += ") << (t == LCU_SOURCE ? "brightness_" : "foreground_") << id
+              << "((struct data_" << id << "*)(data + " << o.d << "), " << (t == LCU_SOURCE ? "y" : "x") << ");\n";
+            first_light = false;
+        }
     }
     if(trigger == LCU_LENS)
         s << "        y" << DEFLECT << "    }\n";
@@ -417,6 +428,25 @@ std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
             o.push_back(tok);
     }
     return o;
+}
+
+bool lcu_ctx::compile(const std::string& source, unsigned flags, std::vector<char>* cubin, std::string* log)
+{
+    std::string key;
+    for(const std::string& o : build_options(flags))
+        key += o + '\n';
+    key += source;
+    auto it = cubins.find(key);
+    if(it != cubins.end())
+    {
+        *cubin = it->second;
+        log->clear();
+        return true;
+    }
+    if(!lcu::compile_cubin(source, headers(), build_options(flags), cubin, log))
+        return false;
+    cubins.emplace(std::move(key), *cubin);
+    return true;
 }
 
 const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)

@@ -157,7 +157,7 @@ struct lcu_model
 
     // device state
     CUmodule mod = nullptr;
-    CUfunction f_set = nullptr, f_render[4] = { nullptr, nullptr, nullptr, nullptr }, f_conv = nullptr, f_reduce = nullptr;
+    CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_reduce = nullptr;
     CUdeviceptr c_objs = 0;
     cudaStream_t stream = nullptr;
     float *d_image = nullptr, *d_weight = nullptr;
@@ -316,7 +316,8 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         const int idx = split == 1 ? 0 : split == 2 ? 1 : split == 4 ? 2 : 3;
         const size_t ppb = 256/split;
         void* args[] = { &a };
-        int rc = launch(m, m->f_render[idx], dim3((unsigned)div_up(nk, ppb), (unsigned)nb), dim3(256), args, st);
+        int rc = launch(m, a.error ? m->f_render_err[idx] : m->f_render[idx], dim3((unsigned)div_up(nk, ppb), (unsigned)nb),
+                        dim3(256), args, st);
         if(rc) return rc;
     }
     if(ev) cudaEventRecord(ev[2], st);
@@ -729,7 +730,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
         m->source = s.str();
     }
 
-    if(!compile_cubin(m->source, ctx->headers(), ctx->build_options(m->flags), &m->cubin, &m->log))
+    if(!ctx->compile(m->source, m->flags, &m->cubin, &m->log))
     {
         set_error("failed to build program\n%s", m->log.c_str());
         delete m;
@@ -754,6 +755,10 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[1], m->mod, "lcu_render_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[2], m->mod, "lcu_render_s4")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[3], m->mod, "lcu_render_s8")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[0], m->mod, "lcu_render_err_s1")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[1], m->mod, "lcu_render_err_s2")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[2], m->mod, "lcu_render_err_s4")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[3], m->mod, "lcu_render_err_s8")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
     if(m->has_psf)
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv, m->mod, "lcu_convolve")));

@@ -1,0 +1,347 @@
+"""Host side around the device path: what a sampler driver needs to run a
+Lensed configuration file against the CUDA layer.
+
+Mirrors, in Python, the small amount of host logic that sits on either side of
+the hot path in the reference (SURVEY.md section 8f "next" rows):
+
+* priors ``delta``/``unif``/``norm``           src/prior.c:70-160, src/prior/*.c
+* ini reader for [options]/[objects]/[priors]  src/input/ini.c:109-284,
+  incl. the ``wrap`` / ``image`` keywords       src/input/objects.c:328-359
+* parameter list, default bounds, parameter map (free dimensions first,
+  derived ones last)                            src/lensed.c:107-271
+* unit cube -> physical -> float32 params       src/nested.c:43-74
+* dumper layers IMG RES RAW ERR WHT PVL         src/nested.c:219-253
+
+Nothing here is on the timed path (O(npar) doubles per evaluation).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import fits
+from .api import Context, Model
+
+POSITION_X, POSITION_Y, RADIUS, MAGNITUDE, AXIS_RATIO, POS_ANGLE = 1, 2, 3, 4, 5, 6
+
+
+# ---------------------------------------------------------------------------
+# priors
+# ---------------------------------------------------------------------------
+class Prior:
+    pseudo = False
+
+    def apply(self, u: float) -> float:
+        raise NotImplementedError
+
+    def lower(self) -> float:
+        raise NotImplementedError
+
+    def upper(self) -> float:
+        raise NotImplementedError
+
+
+class Delta(Prior):
+    """Fixed value = pseudo-prior: the parameter is derived, not sampled
+    (src/prior/delta.c:50-63, src/prior.c PRIORS[0].pseudo)."""
+    pseudo = True
+
+    def __init__(self, value: float):
+        self.value = float(value)
+
+    def apply(self, u):
+        return self.value
+
+    def lower(self):
+        return self.value
+
+    def upper(self):
+        return self.value
+
+
+class Uniform(Prior):
+    def __init__(self, a: float, b: float):
+        self.a, self.b = float(a), float(b)
+
+    def apply(self, u):
+        return self.a + u*(self.b - self.a)          # src/prior/unif.c:68-73
+
+    def lower(self):
+        return self.a
+
+    def upper(self):
+        return self.b
+
+
+class Normal(Prior):
+    def __init__(self, mean: float, sigma: float):
+        self.m, self.s = float(mean), float(sigma)
+
+    @staticmethod
+    def _gauss(u: float) -> float:
+        # rational approximation of the normal quantile (Abramowitz & Stegun
+        # 26.2.23), as src/prior/norm.c:9-15
+        t = math.sqrt(-2.0*math.log(u)) if u < 0.5 else math.sqrt(-2.0*math.log(1 - u))
+        t = t - ((0.010328*t + 0.802853)*t + 2.515517)/(((0.001308*t + 0.189269)*t + 1.432788)*t + 1.0)
+        return -t if u < 0.5 else t
+
+    def apply(self, u):
+        return self.m + self.s*self._gauss(u)         # src/prior/norm.c:77-82
+
+    def lower(self):
+        return self.m - 7*self.s
+
+    def upper(self):
+        return self.m + 7*self.s
+
+
+def read_prior(spec: str) -> Prior:
+    """``"1.5"`` -> delta, ``"unif a b"``, ``"norm m s"`` (src/prior.c:70-160)."""
+    args = spec.split()
+    if len(args) == 1:
+        try:
+            return Delta(float(args[0]))
+        except ValueError:
+            pass
+    if not args:
+        raise ValueError("empty prior")
+    if args[0] == "unif" and len(args) == 3:
+        return Uniform(float(args[1]), float(args[2]))
+    if args[0] == "norm" and len(args) == 3:
+        return Normal(float(args[1]), float(args[2]))
+    if args[0] == "delta" and len(args) == 2:
+        return Delta(float(args[1]))
+    raise ValueError(f"invalid prior definition: {spec}")
+
+
+# ---------------------------------------------------------------------------
+# configuration
+# ---------------------------------------------------------------------------
+@dataclass
+class Parameter:
+    id: str                 # "<object id>.<param name>"
+    name: str
+    type: int
+    lower: float
+    upper: float
+    prior: Optional[Prior] = None
+    wrap: bool = False
+    ipp: bool = False
+    label: Optional[str] = None
+
+    @property
+    def bounded(self) -> bool:
+        return bool(self.lower or self.upper)
+
+    @property
+    def derived(self) -> bool:
+        return self.prior is not None and self.prior.pseudo
+
+
+@dataclass
+class ObjectEntry:
+    id: str
+    name: str
+    type: str
+    params: list = field(default_factory=list)
+
+
+@dataclass
+class Config:
+    options: dict
+    objects: list
+    basedir: str = "."
+
+    @property
+    def parameters(self) -> list:
+        return [p for o in self.objects for p in o.params]
+
+
+def read_ini(path: str, ctx: Context) -> Config:
+    """Parse a Lensed ini file (groups [options] (default) / [objects] /
+    [priors] / [labels]).  Object metadata comes from the compiled object
+    files, as src/input/objects.c:15-266 does."""
+    options, objects, by_id = {}, [], {}
+    grp = "options"
+    nplanes, typ = 0, None
+    with open(path) as f:
+        for lineno, raw in enumerate(f, 1):
+            line = raw.split(";")[0].strip()
+            if not line:
+                continue
+            if line.startswith("["):
+                grp = line.strip("[]").strip()
+                continue
+            if "=" not in line:
+                raise ValueError(f"{path}:{lineno}: expected name = value")
+            name, value = (s.strip() for s in line.split("=", 1))
+            if grp == "options":
+                options[name] = value
+            elif grp == "objects":
+                if name in by_id:
+                    raise ValueError(f"{path}:{lineno}: duplicate object name: {name}")
+                info = ctx.object_info(value)
+                obj = ObjectEntry(name, value, info.type)
+                for p in info.params:
+                    par = Parameter(f"{name}.{p.name}", p.name, p.type, p.bounds[0], p.bounds[1])
+                    if p.has_default:
+                        par.prior = Delta(p.defval)       # src/input/objects.c:225-226
+                    obj.params.append(par)
+                # src/input/ini.c:249-260
+                if info.type != typ and info.type != "F":
+                    if info.type == "L":
+                        nplanes += 1
+                        if nplanes > 1:
+                            raise ValueError(f"{path}:{lineno}: multiple lensing planes are not supported")
+                    typ = info.type
+                objects.append(obj)
+                by_id[name] = obj
+            elif grp in ("priors", "labels"):
+                if "." not in name:
+                    raise ValueError(f"{path}:{lineno}: object {name}: no parameter given (should be {name}.<param>)")
+                oid, pname = name.split(".", 1)
+                if oid not in by_id:
+                    raise ValueError(f"{path}:{lineno}: unknown object: {oid} (check [objects] group)")
+                par = next((p for p in by_id[oid].params if p.name == pname), None)
+                if par is None:
+                    raise ValueError(f"{path}:{lineno}: object {oid}: unknown parameter {pname}")
+                if grp == "labels":
+                    par.label = value
+                    continue
+                # keywords, src/input/objects.c:336-353
+                words = value.split()
+                while words and words[0] in ("wrap", "image"):
+                    if words[0] == "wrap":
+                        par.wrap = True
+                    else:
+                        par.ipp = True
+                    words.pop(0)
+                par.prior = read_prior(" ".join(words)) if words else None
+            else:
+                raise ValueError(f"{path}:{lineno}: unknown group [{grp}]")
+    return Config(options, objects, os.path.dirname(os.path.abspath(path)))
+
+
+# ---------------------------------------------------------------------------
+# the likelihood as the sampler sees it
+# ---------------------------------------------------------------------------
+class Likelihood:
+    """Parameter bookkeeping of src/lensed.c:107-271 plus loglike() of
+    src/nested.c:17-131 on top of a device ``Model``."""
+
+    def __init__(self, cfg: Config, model: Model):
+        self.cfg = cfg
+        self.model = model
+        self.pars = cfg.parameters
+        for p in self.pars:
+            if p.prior is None:
+                raise ValueError(f"missing prior: {p.id}")
+            # default bounds, src/lensed.c:148-167
+            if not p.lower and not p.upper:
+                if p.type == RADIUS:
+                    p.lower, p.upper = 0.0, math.inf
+                elif p.type == AXIS_RATIO:
+                    p.lower, p.upper = 0.0, 1.0
+            if p.bounded and (p.prior.lower() >= p.upper or p.prior.upper() <= p.lower):
+                raise ValueError(f"{p.id}: prior does not include parameter bounds [{p.lower:g}, {p.upper:g}]")
+        free = [i for i, p in enumerate(self.pars) if not p.derived]
+        derived = [i for i, p in enumerate(self.pars) if p.derived]
+        self.pmap = free + derived           # MultiNest keeps derived parameters last
+        self.ndims = len(free)
+        self.npars = len(self.pars)
+
+    def physical(self, cube) -> np.ndarray:
+        """Unit cube (first ndims entries used) -> physical parameters in
+        sampler order (src/nested.c:43-61)."""
+        out = np.empty(self.npars, np.float64)
+        for i in range(self.npars):
+            par = self.pars[self.pmap[i]]
+            u = float(cube[i]) if i < self.ndims else 0.5
+            phys = par.prior.apply(u)
+            if par.bounded and (phys < par.lower or phys > par.upper):
+                # the reference redraws with the same u, i.e. spins forever;
+                # report instead
+                raise ValueError(f"{par.id}: value {phys:g} outside parameter bounds [{par.lower:g}, {par.upper:g}]")
+            out[i] = phys
+        return out
+
+    def device_params(self, phys) -> np.ndarray:
+        """Sampler order -> object order, narrowed to float32 (src/nested.c:70-72)."""
+        params = np.empty(self.npars, np.float32)
+        for i in range(self.npars):
+            params[self.pmap[i]] = phys[i]
+        return params
+
+    def __call__(self, cube) -> float:
+        return self.model.loglike(self.device_params(self.physical(cube)))
+
+    def batch(self, cubes) -> np.ndarray:
+        """Many points per launch: the batched entry point."""
+        P = np.stack([self.device_params(self.physical(c)) for c in cubes])
+        return self.model.loglike_batch(P)
+
+
+def build(path: str, ctx: Context, **model_kw):
+    """ini file -> (Config, Model, Likelihood): reads the image (with section),
+    weight or gain/offset, mask-free, PSF (normalised as src/data.c:354-370)."""
+    from . import workloads
+    cfg = read_ini(path, ctx)
+    opt = cfg.options
+
+    def rel(p):
+        return p if os.path.isabs(p) else os.path.join(cfg.basedir, p)
+
+    image, pcs = fits.read_image(rel(opt["image"]))
+    if "bscale" in opt:
+        image = (image*np.float32(float(opt["bscale"]))).astype(np.float32)
+
+    def value_or_file(v):
+        try:
+            return np.full(image.shape, float(v), np.float32)
+        except ValueError:
+            arr, _ = fits.read_image(rel(v))
+            if arr.shape != image.shape:
+                raise ValueError(f"{v}: wrong dimensions {arr.shape[1]} x {arr.shape[0]}")
+            return arr
+
+    if "weight" in opt:
+        weight = value_or_file(opt["weight"])
+    else:
+        gain = value_or_file(opt.get("gain", "1"))
+        # make_weight(), src/data.c:314-330
+        weight = (gain.astype(np.float64)/(image.astype(np.float64) + float(opt.get("offset", 0)))).astype(np.float32)
+    if "xweight" in opt:
+        weight = weight*value_or_file(opt["xweight"])
+    psf = None
+    if "psf" in opt:
+        psf, _ = fits.read_image(rel(opt["psf"]))
+        psf = workloads.normalise_psf(psf)
+    ipp = [[int(p.ipp) for p in o.params] for o in cfg.objects]
+    model = Model(ctx, [o.name for o in cfg.objects], image, weight, rule=opt.get("rule", "g3k7"), psf=psf, pcs=pcs,
+                  ipp=ipp, **model_kw)
+    return cfg, model, Likelihood(cfg, model)
+
+
+# ---------------------------------------------------------------------------
+# dumper
+# ---------------------------------------------------------------------------
+def dumper_layers(model: Model, params, image, weight) -> dict:
+    """The six result layers of src/nested.c:219-253 for one parameter point."""
+    out = model.render(params)
+    img = out["model"]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        relerr = (out["error"]/out["raw"]).astype(np.float32)
+    pvl = np.array([math.erfc(math.sqrt(0.5*c)) for c in out["chi"].ravel().tolist()], np.float32).reshape(img.shape)
+    return {"IMG": img, "RES": (np.asarray(image, np.float32) - img).astype(np.float32), "RAW": out["raw"], "ERR": relerr,
+            "WHT": np.asarray(weight, np.float32), "PVL": pvl}
+
+
+def write_results(path: str, layers: dict):
+    """Results file: primary HDU + IMAGE extensions named like the reference's
+    (src/data.c:129-165, 372-391)."""
+    names = ["IMG", "RES", "RAW", "ERR", "WHT", "PVL"]
+    fits.write_layers(path, [layers[n] for n in names], names)

@@ -94,7 +94,9 @@ lcu_set_params(int B, const float* __restrict__ params, uint* __restrict__ objs)
 // quadrature points staged per chunk when several warps share a pixel group
 #define LCU_CHUNK 32
 
-template<int S>
+// ERR: also accumulate the quadrature error estimate (second weight); only
+// the dumper asks for it, the likelihood path does not pay for it
+template<int S, bool ERR>
 __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 {
     constexpr int P = LCU_BLOCK/S;          // pixels per block
@@ -137,7 +139,8 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
                 const float4 q = lcu_quad[n];
                 const float c = lcu_compute(data, float2(__fadd_rn(x.x, q.x), __fadd_rn(x.y, q.y)));
                 f0 = __fadd_rn(f0, __fmul_rn(q.z, c));
-                f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
+                if(ERR)
+                    f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
             }
         }
     }
@@ -165,7 +168,8 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
                     const float4 q = lcu_quad[n];
                     const float c = sc[pl][n - c0];
                     f0 = __fadd_rn(f0, __fmul_rn(q.z, c));
-                    f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
+                    if(ERR)
+                        f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
                 }
             }
             __syncthreads();
@@ -182,7 +186,7 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     {
         if(a.mode & LCU_OUT_VALUE)
             a.value[o] = f0;
-        if(a.mode & LCU_OUT_ERROR)
+        if(ERR && (a.mode & LCU_OUT_ERROR))
             a.error[o] = f1;
         if(a.mode & (LCU_OUT_CHI2 | LCU_OUT_CHIMAP))
         {
@@ -205,17 +209,15 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     }
 }
 
-extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
-lcu_render_s1(const __grid_constant__ lcu_render_args a) { lcu_render_impl<1>(a); }
-
-extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
-lcu_render_s2(const __grid_constant__ lcu_render_args a) { lcu_render_impl<2>(a); }
-
-extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
-lcu_render_s4(const __grid_constant__ lcu_render_args a) { lcu_render_impl<4>(a); }
-
-extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
-lcu_render_s8(const __grid_constant__ lcu_render_args a) { lcu_render_impl<8>(a); }
+#define LCU_RENDER_KERNEL(S) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK) \
+    lcu_render_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, false>(a); } \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK) \
+    lcu_render_err_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, true>(a); }
+LCU_RENDER_KERNEL(1)
+LCU_RENDER_KERNEL(2)
+LCU_RENDER_KERNEL(4)
+LCU_RENDER_KERNEL(8)
 
 // ---------------------------------------------------------------------------
 // convolve + chi^2

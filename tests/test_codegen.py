@@ -18,8 +18,9 @@ def test_compute_order_host_lens_source_sky(compile_ctx):
     m = L.Model(compile_ctx, ["sersic", "sie", "sersic", "sky"], IMG, IMG)
     body = _body(m.source, "float lcu_compute(")
     lines = [l.strip() for l in body.splitlines() if "+=" in l or "-=" in l]
-    assert lines[0].startswith("f += brightness_sersic((struct data_sersic*)(data + 0), y)")       # unlensed host
-    assert lines[1].startswith("a += deflection_sie((struct data_sie*)(data + 12), y)")
+    lines = [l.strip() for l in body.splitlines() if " = " in l and ("deflection_" in l or "brightness_" in l or "foreground_" in l) or "+=" in l or "-=" in l]
+    assert lines[0].startswith("f = brightness_sersic((struct data_sersic*)(data + 0), y)")        # unlensed host
+    assert lines[1].startswith("a = deflection_sie((struct data_sie*)(data + 12), y)")
     assert lines[2].startswith("y -= dot(a, a) < HUGE_VALF ? a : lcu_float2(1E10f, 1E10f)")        # non-finite guard
     assert lines[3].startswith("f += brightness_sersic((struct data_sersic*)(data + 28), y)")      # lensed source
     assert lines[4].startswith("f += foreground_sky((struct data_sky*)(data + 40), x)")            # image plane
