@@ -107,6 +107,12 @@ def cpu_library():
 def cpu_model(w, image, weight):
     from oracle import pyoracle as O
     lib, kind = cpu_library()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    lib.orc_set_threads(ncpu)
     qq, ww = O.quad_rule(w["rule"])
     return O.Model(w["objects"], image, weight, qq, ww, psf=w["psf"], _lib=lib), lib, kind
 
@@ -175,6 +181,9 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO prints to stdout; this program prints one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = workload(args.workload)

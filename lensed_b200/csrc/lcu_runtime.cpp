@@ -169,6 +169,12 @@ struct lcu_model
     float *d_params = nullptr, *h_params = nullptr;
     double *d_lnew = nullptr, *h_lnew = nullptr;
     size_t stage_cap = 0;
+    // single-point evaluation (the sampler's one-point callback) as a CUDA graph:
+    // upload, 3-4 kernels, constant-bank copy and read-back replayed by one launch
+    cudaGraphExec_t graph1 = nullptr;
+    bool graph1_off = false;
+    size_t graph1_rows[2] = { 0, 0 };
+    int graph1_split = 0;
     // dumper buffers (one point), allocated on first lcu_render
     float *d_value1 = nullptr, *d_error1 = nullptr, *d_model1 = nullptr, *d_chi1 = nullptr;
     // profiling: one set of stage events per launched chunk, harvested lazily
@@ -233,6 +239,12 @@ int ensure_stage(lcu_model* m, size_t nbatch)
 {
     if(nbatch <= m->stage_cap)
         return LCU_OK;
+    if(m->graph1)
+    {
+        // the single-point graph refers to the staging buffers
+        cudaGraphExecDestroy(m->graph1);
+        m->graph1 = nullptr;
+    }
     if(m->d_params) cudaFree(m->d_params);
     if(m->d_lnew) cudaFree(m->d_lnew);
     if(m->h_params) cudaFreeHost(m->h_params);
@@ -409,10 +421,58 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
     return LCU_OK;
 }
 
+// (re)build the single-point graph if the launch configuration changed;
+// returns false when graphs are unavailable (the plain path is used then)
+bool single_point_graph(lcu_model* m)
+{
+    if(m->graph1_off)
+        return false;
+    const char* forced = getenv("LCU_SPLIT");
+    const int split = forced && *forced ? atoi(forced) : 0;
+    if(m->graph1 && m->graph1_rows[0] == m->row0 && m->graph1_rows[1] == m->row1 && m->graph1_split == split)
+        return true;
+    if(m->graph1)
+    {
+        cudaGraphExecDestroy(m->graph1);
+        m->graph1 = nullptr;
+    }
+    if(getenv("LCU_NO_GRAPH") || ensure_partial(m) != LCU_OK)
+    {
+        m->graph1_off = true;
+        return false;
+    }
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if(ok)
+    {
+        ok = cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
+        ok = ok && enqueue_batch(m, 1, m->d_params, m->d_lnew, m->stream) == LCU_OK;
+        ok = ok && cudaMemcpyAsync(m->h_lnew, m->d_lnew, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+        ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
+    }
+    if(ok)
+        ok = cudaGraphInstantiate(&m->graph1, graph, 0) == cudaSuccess;
+    if(graph)
+        cudaGraphDestroy(graph);
+    if(!ok)
+    {
+        cudaGetLastError();
+        m->graph1 = nullptr;
+        m->graph1_off = true;
+        return false;
+    }
+    m->graph1_rows[0] = m->row0;
+    m->graph1_rows[1] = m->row1;
+    m->graph1_split = split;
+    return true;
+}
+
 void destroy_device_state(lcu_model* m)
 {
     if(m->ctx && m->ctx->device >= 0)
         cudaSetDevice(m->ctx->device);
+    if(m->graph1)
+        cudaGraphExecDestroy(m->graph1);
     for(cudaEvent_t& e : m->ev_io)
         if(e) { cudaEventDestroy(e); e = nullptr; }
     for(lcu_model::EventSet& es : m->evsets)
@@ -886,6 +946,17 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
     rc = ensure_stage(m, nbatch);
     if(rc) return rc;
     cudaEvent_t* ev = m->profile ? m->ev_io : nullptr;
+
+    // the sampler's one-point call: one graph launch instead of 7 API calls
+    if(nbatch == 1 && !m->profile && single_point_graph(m))
+    {
+        memcpy(m->h_params, params, m->npars*sizeof(float));
+        RT_CHECK(cudaGraphLaunch(m->graph1, m->stream));
+        g_launches.fetch_add(m->has_psf ? 4 : 3, std::memory_order_relaxed);
+        RT_CHECK(cudaStreamSynchronize(m->stream));
+        *lnew = m->h_lnew[0];
+        return LCU_OK;
+    }
 
     // parameter upload, src/nested.c:67-74
     memcpy(m->h_params, params, nbatch*m->npars*sizeof(float));

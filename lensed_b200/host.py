@@ -246,8 +246,11 @@ class Likelihood:
                     p.lower, p.upper = 0.0, math.inf
                 elif p.type == AXIS_RATIO:
                     p.lower, p.upper = 0.0, 1.0
-            if p.bounded and (p.prior.lower() >= p.upper or p.prior.upper() <= p.lower):
-                raise ValueError(f"{p.id}: prior does not include parameter bounds [{p.lower:g}, {p.upper:g}]")
+            # src/lensed.c:172-190: only a prior reaching outside the bounds is
+            # examined; no overlap at all is an error, partial overlap a warning
+            if p.bounded and (p.prior.lower() < p.lower or p.prior.upper() > p.upper):
+                if p.prior.lower() >= p.upper or p.prior.upper() <= p.lower:
+                    raise ValueError(f"{p.id}: prior does not include parameter bounds [{p.lower:g}, {p.upper:g}]")
         free = [i for i, p in enumerate(self.pars) if not p.derived]
         derived = [i for i, p in enumerate(self.pars) if p.derived]
         self.pmap = free + derived           # MultiNest keeps derived parameters last

@@ -209,10 +209,18 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     }
 }
 
+// Resident blocks per SM the compiler budgets registers for: 3 (<= 85
+// registers, 24 warps/SM) lets it keep every object field of the ray loop in
+// registers; the kernel is issue-bound with ~5 eligible warps per scheduler,
+// so the lower occupancy costs nothing (profiles/).
+#ifndef LCU_RENDER_MINBLOCKS
+#define LCU_RENDER_MINBLOCKS 3
+#endif
+
 #define LCU_RENDER_KERNEL(S) \
-    extern "C" __global__ void __launch_bounds__(LCU_BLOCK) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
     lcu_render_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, false>(a); } \
-    extern "C" __global__ void __launch_bounds__(LCU_BLOCK) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
     lcu_render_err_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, true>(a); }
 LCU_RENDER_KERNEL(1)
 LCU_RENDER_KERNEL(2)

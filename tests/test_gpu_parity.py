@@ -252,3 +252,61 @@ def test_full_size_c4_properties(gpu_ctx):
     value, _ = band.oracle().render(cfg.params)
     r = H.rel_err(out["raw"][480:544], value)
     assert r.max() <= PIXEL_TOL, f"band max rel err {r.max():.3e}"
+
+
+def test_non_finite_deflection_guard(gpu_ctx):
+    """A ray that hits a singular lens centre exactly has a NaN deflection
+    (0/0); compute() then throws it to (1e10, 1e10) (src/kernel.c:86-91) and it
+    contributes the source's (vanishing) brightness there plus the sky."""
+    img = np.zeros((9, 9), np.float32)
+    for lens, lp in (("sis", [5.0, 5.0, 2.0]), ("point_mass", [5.0, 5.0, 2.0]), ("sis_plus_shear", [5.0, 5.0, 2.0, 0.1, 0.0])):
+        params = np.array(lp + [5.0, 5.0, 1.5, -2.0, 1.0, 0.9, 10.0] + [0.25, 0.0, 0.0], np.float32)
+        cfg = H.Config("guard-" + lens, [lens, "sersic", "sky"], params, img, np.ones_like(img), rule="point")
+        om, m = cfg.oracle(), cfg.product(gpu_ctx)
+        value, _ = om.render(params)
+        out = m.render(params)
+        assert np.isfinite(out["raw"]).all()
+        assert out["raw"][4, 4] == np.float32(0.25) == value[4, 4]        # centre pixel: sky only
+        assert H.rel_err(out["raw"], value).max() <= PIXEL_TOL
+
+
+def test_empty_and_ragged_batches(gpu_ctx):
+    cfg = H.synthetic_config("c4", 40, psf_shape=(3, 7))
+    m = cfg.product(gpu_ctx, max_batch=4)
+    assert m.loglike_batch(np.zeros((0, m.npars), np.float32)).shape == (0,)
+    P = H.workloads.param_batch(cfg.extra["workload"], 11)          # 4 + 4 + 3
+    got = m.loglike_batch(P)
+    ref = np.array([cfg.oracle().loglike(p) for p in P])
+    assert np.all(np.abs(got - ref) <= 3*LOGLIKE_TOL*np.abs(ref))
+    with pytest.raises(ValueError):
+        m.loglike_batch(np.zeros((3, m.npars + 1), np.float32))
+
+
+def test_full_size_c5_properties(gpu_ctx):
+    """4096^2 / epl_plus_shear + 3 sersic + sky / g3k7 / 25x25 PSF."""
+    w = H.workloads.c5(4096)
+    img = np.zeros((4096, 4096), np.float32)
+    m0 = H.Config("C5", w["objects"], w["truth"], img, np.ones_like(img), rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=4)
+    model = m0.render(w["truth"], raw=False, error=False, chi=False)["model"]
+    m0.close()
+    image, weight = H.workloads.observe(model, w["noise_seed"])
+    m = H.Config("C5", w["objects"], w["truth"], image, weight, rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=4)
+    full = m.loglike(w["truth"])
+    assert 0.9 < -2*full/image.size < 1.1
+    parts = []
+    for r0, r1 in ((0, 1000), (1000, 1001), (1001, 4096)):
+        m.set_rows(r0, r1)
+        parts.append(m.loglike(w["truth"]))
+    assert abs(sum(parts) - full) <= 1e-12*abs(full)
+    m.set_rows(0, 4096)
+    P = H.workloads.param_batch(w, 3)
+    assert np.array_equal(m.loglike_batch(P), np.array([m.loglike(p) for p in P]))
+    # banded oracle check of 32 rows through the lens centre (pre-PSF image)
+    raw = m.render(w["truth"], model=False, error=False, chi=False)["raw"]
+    band = H.Config("C5-band", w["objects"], w["truth"], np.zeros((32, 4096), np.float32), np.ones((32, 4096), np.float32),
+                    rule=w["rule"], pcs=(1.0, 2033.0, 1.0, 1.0))
+    value, _ = band.oracle().render(w["truth"])
+    v64, _ = band.oracle(variant="f64").render(w["truth"])
+    r = H.rel_err(raw[2032:2064], value)
+    floor = H.rel_err(value, v64).max()
+    assert np.quantile(r, 0.999) <= PIXEL_TOL and r.max() <= max(PIXEL_TOL, 1.5*floor), f"{r.max():.3e} floor {floor:.3e}"

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Single-point latency of lcu_loglike (the sampler's one-point callback) on the
+reference's example-sized images, with and without the CUDA-graph path, next to
+the reference CPU build.  Writes gpurun_out/latency.json."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import lensed_b200 as L
+import helpers as H
+
+out = {}
+ctx = L.Context(device=0)
+for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
+    cfg = H.example_config(name)
+    res = {}
+    for mode in ("graph", "plain"):
+        if mode == "plain":
+            os.environ["LCU_NO_GRAPH"] = "1"
+        else:
+            os.environ.pop("LCU_NO_GRAPH", None)
+        m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS)
+        for _ in range(20):
+            v = m.loglike(cfg.params)
+        n = 2000
+        t0 = time.perf_counter()
+        for _ in range(n):
+            v = m.loglike(cfg.params)
+        dt = (time.perf_counter() - t0)/n
+        res[mode] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, lnew=v)
+        m.close()
+    assert res["graph"]["lnew"] == res["plain"]["lnew"]
+    try:
+        om = cfg.oracle(variant="ref_fast")
+        om.loglike(cfg.params)
+        n = 200
+        t0 = time.perf_counter()
+        for _ in range(n):
+            om.loglike(cfg.params)
+        dt = (time.perf_counter() - t0)/n
+        res["cpu_reference"] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, threads=om.L.orc_max_threads())
+    except Exception as e:
+        res["cpu_reference"] = repr(e)
+    out[name] = res
+    print(name, json.dumps(res), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "latency.json"), "w"), indent=1)
