@@ -130,6 +130,8 @@ typedef struct
 #define LCU_FAST_INTRINSICS 4u  /* exp/log/pow/sin/cos -> hardware exp2/log2/sin/cos
                                    approximations in SOURCE and FOREGROUND objects */
 #define LCU_FAST_LENS_INTRINSICS 16u /* the same in LENS objects (less accurate deflections) */
+#define LCU_FAST_ATANH      32u /* atanh in LENS objects = (ln(1+x) - ln(1-x))/2 on the hardware
+                                   log2: absolute error 2e-7 (isothermal ellipsoid deflections) */
 #define LCU_FAST_DIVSQRT    8u  /* approximate division and square root (2 ulp) */
 
 typedef struct

@@ -87,6 +87,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "//----------------------------------------------------------------------------\n"
       << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
       << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"
+      << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_ON\n#include \"shim.cuh\"\n#endif\n"
       << "#define type const int type_" << id << "\n"
       << "#define params extern \"C\" __device__ const struct param lcu_parlst_" << id << "[] = \n"
       << "#define data struct data_" << id << "\n"
@@ -99,6 +100,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "#undef type\n#undef params\n#undef data\n#undef deflection\n"
       << "#undef brightness\n#undef foreground\n#undef set\n"
       << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_OFF\n#include \"shim.cuh\"\n#endif\n"
+      << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_OFF\n#include \"shim.cuh\"\n#endif\n"
       << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
       << "extern \"C\" __device__ const unsigned int lcu_meta_" << id << "[3] = {\n"
       << "    (unsigned int)type_" << id << ",\n"
@@ -402,7 +404,9 @@ std::vector<lcu::Header> lcu_ctx::headers() const
 // for exp/log/pow/sin/cos in source and foreground objects (remapped at source
 // level by shim.cuh; measured as accurate as the strict build on Sersic
 // scenes), LCU_FAST_LENS_INTRINSICS = the same in lens objects (costs accuracy
-// in the deflection), LCU_FAST_DIVSQRT = approximate division and square root.
+// in the deflection), LCU_FAST_ATANH = atanh of lens objects on the hardware
+// log2 (absolute error 2e-7), LCU_FAST_DIVSQRT = approximate division and
+// square root.
 // Denormals are flushed either way.
 std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
 {
@@ -415,6 +419,8 @@ std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
     };
     o.push_back((flags & LCU_FAST_INTRINSICS) ? "-DLCU_INTRINSICS_SOURCE=1" : "-DLCU_INTRINSICS_SOURCE=0");
     o.push_back((flags & LCU_FAST_LENS_INTRINSICS) ? "-DLCU_INTRINSICS_LENS=1" : "-DLCU_INTRINSICS_LENS=0");
+    o.push_back((flags & LCU_FAST_ATANH) ? "-DLCU_ATANH_LENS=1" : "-DLCU_ATANH_LENS=0");
+    o.push_back("-DLCU_ATANH_SOURCE=0");
     o.push_back("--ftz=true");
     o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-div=false" : "--prec-div=true");
     o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-sqrt=false" : "--prec-sqrt=true");
