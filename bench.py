@@ -189,7 +189,7 @@ def run_gpu(args):
     w = workload(args.workload)
     ctx = L.Context(device=local)
     image, weight = synthetic_observation(w, ctx)
-    flags = 0 if args.math == "strict" else L.LCU_FAST_INTRINSICS
+    flags = 0 if args.math == "strict" else (L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
     model = L.Model(ctx, w["objects"], image, weight, rule=w["rule"], psf=w["psf"], flags=flags)
     B = args.batch
     nq = model.nq
@@ -281,8 +281,9 @@ def run_gpu(args):
             "config": {"workload": f"{w['name']}: {'+'.join(w['objects'])}, {w['width']}x{w['height']}, PSF 25x25, rule {w['rule']}",
                        "points_per_gpu_per_step": B, "rays_per_eval": work["rays"], "parallelism": f"points x{world}",
                        "math": "strict: IEEE ops in source order, accurate libdevice functions, no FMA contraction" if flags == 0 else
-                               "LCU_FAST_INTRINSICS: hardware exp2/log2 in source/foreground objects; lens deflections, division, "
-                               "sqrt and summation order as in the strict build (parity-tested to the same bounds)",
+                               "LCU_FAST_INTRINSICS|LCU_FAST_ATANH: exp/log of source and foreground objects and atanh of lens objects "
+                               "on the hardware exp2/log2 units; division, sqrt, atan, no FMA contraction and the summation order "
+                               "as in the strict build (parity-tested to the same bounds, tests/test_gpu_parity.py)",
                        "l2": f"working set per step {(B*w['width']*w['height']*4 + 8*w['width']*w['height'])/1e6:.0f} MB of staged "
                              "images > 126 MB L2 (no explicit flush)" if B*w['width']*w['height']*4 > 126e6 else
                              "compute-bound kernel, working set fits L2; inputs re-read from L2 by design"},
@@ -345,7 +346,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"])
     ap.add_argument("--batch", type=int, default=32, help="parameter points per GPU per step")
-    ap.add_argument("--math", default="fast-sources", choices=["strict", "fast-sources"])
+    ap.add_argument("--math", default="fast", choices=["strict", "fast"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

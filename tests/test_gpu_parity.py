@@ -17,10 +17,13 @@ PIXEL_TOL = 1e-5
 LOGLIKE_TOL = 1e-6
 
 # build modes under test: the default (one IEEE operation per source operation,
-# accurate libdevice functions) and LCU_FAST_INTRINSICS (hardware exp2/log2 in
-# source/foreground objects only) which bench.py uses -- "fast-math only where
-# the reference's tolerance allows": both have to meet the same bounds
-MATH_MODES = [pytest.param(0, id="strict"), pytest.param(4, id="fast-sources")]
+# accurate libdevice functions) and the relaxed build bench.py runs,
+# LCU_FAST_INTRINSICS | LCU_FAST_ATANH: exp / log of source and foreground
+# objects on the hardware exp2 / log2 units (compensated arguments), atanh of
+# lens objects on the hardware log2 -- "fast-math only where the reference's
+# tolerance allows": both have to meet the same bounds
+FAST = 4 | 32
+MATH_MODES = [pytest.param(0, id="strict"), pytest.param(FAST, id="fast")]
 
 
 def _lnew_tol(cfg, params, lnew, base=LOGLIKE_TOL):
@@ -286,11 +289,11 @@ def test_full_size_c5_properties(gpu_ctx):
     """4096^2 / epl_plus_shear + 3 sersic + sky / g3k7 / 25x25 PSF."""
     w = H.workloads.c5(4096)
     img = np.zeros((4096, 4096), np.float32)
-    m0 = H.Config("C5", w["objects"], w["truth"], img, np.ones_like(img), rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=4)
+    m0 = H.Config("C5", w["objects"], w["truth"], img, np.ones_like(img), rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=FAST)
     model = m0.render(w["truth"], raw=False, error=False, chi=False)["model"]
     m0.close()
     image, weight = H.workloads.observe(model, w["noise_seed"])
-    m = H.Config("C5", w["objects"], w["truth"], image, weight, rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=4)
+    m = H.Config("C5", w["objects"], w["truth"], image, weight, rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=FAST)
     full = m.loglike(w["truth"])
     assert 0.9 < -2*full/image.size < 1.1
     parts = []
@@ -310,3 +313,33 @@ def test_full_size_c5_properties(gpu_ctx):
     r = H.rel_err(raw[2032:2064], value)
     floor = H.rel_err(value, v64).max()
     assert np.quantile(r, 0.999) <= PIXEL_TOL and r.max() <= max(PIXEL_TOL, 1.5*floor), f"{r.max():.3e} floor {floor:.3e}"
+
+
+def test_single_point_graph_and_profile(gpu_ctx, monkeypatch):
+    """The one-point entry replays a CUDA graph; it must return exactly what
+    the plain launch sequence returns, also after the row range changes, and
+    the per-stage profile must account for every evaluation."""
+    import lensed_b200 as L
+    cfg = H.example_config("full_mock_psf")
+    m = cfg.product(gpu_ctx)
+    P = np.stack([cfg.params*(1 + 1e-3*i) for i in range(4)]).astype(np.float32)
+    batch = m.loglike_batch(P)
+    n0 = L.launch_count()
+    single = np.array([m.loglike(p) for p in P])           # graph path
+    assert np.array_equal(single, batch)
+    assert L.launch_count() - n0 >= 4*4                      # set_params, render, convolve, reduce per point
+    monkeypatch.setenv("LCU_NO_GRAPH", "1")
+    m2 = cfg.product(gpu_ctx)
+    assert np.array_equal(np.array([m2.loglike(p) for p in P]), batch)
+    monkeypatch.delenv("LCU_NO_GRAPH")
+    m.set_rows(10, 60)
+    a = m.loglike(P[0])
+    m.set_rows(0, cfg.image.shape[0])
+    assert m.loglike(P[0]) == batch[0] and a != batch[0]
+    m.profile(True)
+    m.loglike_batch(P)
+    m.loglike(P[0])
+    pr = m.profile_get()
+    m.profile(False)
+    assert pr["evaluations"] == 5
+    assert pr["render_ms"] > 0 and pr["convolve_ms"] > 0 and pr["reduce_ms"] > 0 and pr["set_params_ms"] > 0

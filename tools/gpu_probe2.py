@@ -20,7 +20,7 @@ for cfg in cfgs:
     lnew, model, _ = om.loglike(cfg.params, want_maps=True)
     refs.append((value, model, lnew))
 out = {}
-for flags in (4, 36, 12, 44, 37):
+for flags in (0, 4, 36):
     worst_raw = worst_model = worst_ln = 0
     for cfg, (value, model, lnew) in zip(cfgs, refs):
         m = cfg.product(ctx, flags=flags)

@@ -19,7 +19,7 @@ for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
             os.environ["LCU_NO_GRAPH"] = "1"
         else:
             os.environ.pop("LCU_NO_GRAPH", None)
-        m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS)
+        m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
         for _ in range(20):
             v = m.loglike(cfg.params)
         n = 2000
