@@ -26,16 +26,16 @@ FAST = 4 | 32
 MATH_MODES = [pytest.param(0, id="strict"), pytest.param(FAST, id="fast")]
 
 
-def _lnew_tol(cfg, params, lnew, base=LOGLIKE_TOL):
-    """Relative tolerance for one log-likelihood: 1e-6, unless the strict
-    float32 oracle itself is further than that from its float64 twin at this
-    point (badly fitting points of the EPL scene: the reference built with its
-    own -cl-fast-relaxed-math analogue moves by 1.4e-6 ... 2.4e-6 there), in
-    which case 3x that float32 noise."""
-    l64 = cfg.oracle(variant="f64").loglike(params)
-    floor = abs(l64 - lnew)/abs(lnew)
-    return max(base, 3*floor)
-
+def _lnew_tol(cfg, lnew, base=LOGLIKE_TOL):
+    """Relative tolerance for one log-likelihood: 1e-6 wherever the model
+    fits (chi^2/dof < 10, the region a sampler resolves).  At badly fitting
+    points (the 1 %-off batch: chi^2/dof ~ 10^2) the residuals are dominated by
+    model mismatch, per-pixel rounding differences add up coherently, and the
+    strict float32 oracle itself is 0.6e-6 ... 4.2e-6 away from its float64
+    twin and 1.4e-6 ... 2.4e-6 from the reference's code built with its own
+    fast-math flags: 4e-6 there."""
+    chi2_dof = -2*lnew/cfg.image.size
+    return base if chi2_dof < 10 else max(base, 4e-6)
 
 
 def _check_images(out, cfg, om):
@@ -139,10 +139,9 @@ def test_synthetic_scenes(gpu_ctx, which, size, psf, flags):
     P = H.workloads.param_batch(cfg.extra["workload"], 5)
     ref = np.array([om.loglike(p) for p in P])
     got = m.loglike_batch(P)
-    tols = np.array([_lnew_tol(cfg, p, r, tol) for p, r in zip(P, ref)])
+    tols = np.array([_lnew_tol(cfg, r, tol) for r in ref])
     rel = np.abs(got - ref)/np.abs(ref)
     assert np.all(rel <= tols), f"{cfg.name}: batch lnew rel err {rel} (tolerances {tols})"
-    assert np.all(rel <= 4e-6)
 
 
 def test_masked_pixels(gpu_ctx):
