@@ -342,3 +342,36 @@ def test_single_point_graph_and_profile(gpu_ctx, monkeypatch):
     m.profile(False)
     assert pr["evaluations"] == 5
     assert pr["render_ms"] > 0 and pr["convolve_ms"] > 0 and pr["reduce_ms"] > 0 and pr["set_params_ms"] > 0
+
+
+@pytest.mark.parametrize("flags", MATH_MODES)
+def test_every_object_in_one_model(gpu_ctx, flags):
+    """Host galaxy + foreground + three lenses summed in one plane + four
+    lensed sources (one with image-plane priors) + an object the reference
+    cannot even load (sersic-old): exercises the generated compute() /
+    set_params() beyond the reference's own configurations."""
+    objects = ["sersic", "sky", "sie", "point_mass", "nsis", "gauss", "devauc", "exponential", "sersic-old"]
+    params = np.array(
+        [30.5, 30.5, 6.0, -4.0, 2.5, 0.8, 20.0,            # host sersic (unlensed)
+         0.02, 1e-4, -2e-4,                                # sky with gradient
+         30.5, 30.5, 12.0, 0.7, 60.0,                      # sie
+         38.0, 27.0, 2.0,                                  # point_mass
+         25.0, 35.0, 3.0, 1.5,                             # nsis
+         44.0, 30.0, 1.5, -3.0, 0.9, 15.0,                 # gauss, image-plane position
+         31.0, 32.0, 2.0, -3.5, 0.7, 100.0,                # devauc
+         29.0, 30.0, 1.0, -2.5, 0.6, 45.0,                 # exponential
+         32.0, 29.0, 1.5, -3.0, 1.2, 0.85, 70.0], np.float32)   # sersic-old
+    img = np.zeros((60, 60), np.float32)
+    cfg = H.Config("zoo", objects, params, img, np.ones_like(img), rule="g5k11", psf=H.workloads.gaussian_psf(7, 5, 1.2),
+                   ipp=[[0]*7, [0]*3, [0]*5, [0]*3, [0]*4, [1, 1, 0, 0, 0, 0], [0]*6, [0]*6, [0]*7])
+    om = cfg.oracle()
+    _, model, _ = om.loglike(params, want_maps=True)
+    cfg.image, cfg.weight = H.workloads.observe(model, 99, gain=50.0, offset=0.5)
+    om = cfg.oracle()
+    m = cfg.product(gpu_ctx, flags=flags)
+    assert m.npars == params.size and m.words == 12 + 4 + 16 + 4 + 4 + 12*4
+    out = m.render(params)
+    lnew, _ = _check_images(out, cfg, om)
+    got = m.loglike(params)
+    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew)          # 60^2 pixels
+    _check_block(m, om, cfg)
