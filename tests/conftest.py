@@ -8,6 +8,23 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_built():
+    """Built artefacts are git-ignored: on a fresh checkout compile the C-ABI
+    library and the oracle before anything imports them (same recipes as
+    __graft_entry__.build)."""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "lensed_b200", "liblensed_cuda.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "lensed_b200", "csrc")], check=True)
+    if not all(os.path.exists(os.path.join(ROOT, "oracle", n)) for n in ("liboracle.so", "liboracle_f64.so", "liboracle_fast.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
+    ref = os.environ.get("LENSED_REFERENCE", "/root/reference")
+    if os.path.isdir(ref) and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liblensed_ref.so")):
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py")], check=False)
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
