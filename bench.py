@@ -37,6 +37,15 @@ sys.path.insert(0, ROOT)
 METRIC = "likelihood_evals_per_s"
 UNIT = "evals/s"
 
+# stdout carries exactly one JSON line: libraries that print to stdout (NCCL's
+# version banner, for one) are sent to stderr for the whole run
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 def peaks():
     try:
@@ -164,7 +173,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -181,8 +190,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (this benchmark has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL_DEBUG=VERSION/INFO prints to stdout; this program prints one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO", "TRACE"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -246,12 +254,22 @@ def run_gpu(args):
     lnew_dev = d_lnew.cpu().numpy().copy()
 
     # ---- timed region: end to end through the host-buffer C-ABI call ---------
+    # (N > 1: through lensed_b200.distributed, which adds the NCCL all-reduce
+    # that assembles the full lnew vector on every rank)
+    from lensed_b200.distributed import ShardedLikelihood
+    sharded = ShardedLikelihood.for_model(model, mode="points", device=f"cuda:{local}") if world > 1 else None
+
+    def host_step():
+        if sharded is None:
+            return model.loglike_batch(P)
+        return sharded.loglike_batch(P_all)[rank*B:(rank + 1)*B]
+
     for _ in range(2):
-        model.loglike_batch(P)
+        host_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        lnew_host = model.loglike_batch(P)
+        lnew_host = host_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -332,7 +350,7 @@ def run_gpu(args):
                 line["parity_lnew_rel"] = abs(lnew_dev[0] - strict)/abs(strict)
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "unavailable", "sample": repr(e)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
