@@ -751,6 +751,24 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
         m->maxb = maxb;
     }
 
+    // Is the rule a Cartesian grid (first axis outer, second inner)?  All
+    // Gauss-Kronrod and sub-sampling rules of src/quad/ are; gm75 is not.
+    size_t quad_ni = 0, quad_nj = 0;
+    for(size_t nj = 2; nj*nj <= m->nq*m->nq && nj <= m->nq/2; ++nj)
+    {
+        if(m->nq % nj)
+            continue;
+        bool grid = true;
+        for(size_t n = 0; n < m->nq && grid; ++n)
+            grid = desc->qq[2*n] == desc->qq[2*((n/nj)*nj)] && desc->qq[2*n + 1] == desc->qq[2*(n%nj) + 1];
+        if(grid)
+        {
+            quad_nj = nj;
+            quad_ni = m->nq/nj;
+            break;
+        }
+    }
+
     // program text: main_program(), src/kernel.c:838-879 -- ABI headers,
     // each distinct object once, compute, set_params, kernels
     {
@@ -763,6 +781,8 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "#define PSF_WIDTH " << m->psfw << "\n"
           << "#define PSF_HEIGHT " << m->psfh << "\n"
           << "#define QUAD_POINTS " << m->nq << "\n"
+          << "#define LCU_QUAD_NI " << quad_ni << "\n"
+          << "#define LCU_QUAD_NJ " << quad_nj << "\n"
           << "#define LCU_WORDS " << m->words << "\n"
           << "#define LCU_NPARS " << std::max<size_t>(m->npars, 1) << "\n"
           << "#define LCU_MAXB " << m->maxb << "\n"

@@ -6,7 +6,8 @@
 // by the host (lcu_program.cpp) after the object plugins and the generated
 // lcu_compute() / lcu_set_params_body(), and compiled with NVRTC.  Macros
 // provided by the host: IMAGE_SIZE IMAGE_WIDTH IMAGE_HEIGHT PSF PSF_WIDTH
-// PSF_HEIGHT QUAD_POINTS (src/kernel.c:890-896 names), LCU_WORDS (object block
+// PSF_HEIGHT QUAD_POINTS (src/kernel.c:890-896 names), LCU_QUAD_NI x LCU_QUAD_NJ
+// (grid shape if the rule is Cartesian, else 0), LCU_WORDS (object block
 // size in 4-byte words), LCU_NPARS, LCU_MAXB (parameter points per launch),
 // LCU_OBJ_CONST (object blocks in the constant bank instead of shared memory).
 //
@@ -133,6 +134,27 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     {
         if(live)
         {
+#if LCU_QUAD_NI > 0
+            // Cartesian rule (first axis outer, second inner, as the tables
+            // are laid out): same points, same order, but written as two
+            // loops so that everything that depends on the x abscissa only
+            // (x - centre, its products with the rotation matrices, ...) is
+            // computed once per grid column instead of once per ray
+#pragma unroll 1
+            for(int i = 0; i < LCU_QUAD_NI; ++i)
+            {
+                const float rx = __fadd_rn(x.x, lcu_quad[i*LCU_QUAD_NJ].x);
+#pragma unroll 1
+                for(int j = 0; j < LCU_QUAD_NJ; ++j)
+                {
+                    const float4 q = lcu_quad[i*LCU_QUAD_NJ + j];
+                    const float c = lcu_compute(data, float2(rx, __fadd_rn(x.y, q.y)));
+                    f0 = __fadd_rn(f0, __fmul_rn(q.z, c));
+                    if(ERR)
+                        f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
+                }
+            }
+#else
 #pragma unroll 1
             for(int n = 0; n < QUAD_POINTS; ++n)
             {
@@ -142,6 +164,7 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
                 if(ERR)
                     f1 = __fadd_rn(f1, __fmul_rn(q.w, c));
             }
+#endif
         }
     }
     else
