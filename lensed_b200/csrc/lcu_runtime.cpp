@@ -162,7 +162,8 @@ struct lcu_model
     cudaStream_t stream = nullptr;
     float *d_image = nullptr, *d_weight = nullptr;
     uint32_t* d_objs = nullptr;         // [maxb][words]
-    float* d_raw = nullptr;             // [maxb][size], PSF models only
+    float* d_raw = nullptr;             // [raw_cap][size] rendered images, PSF models only; grows on demand
+    size_t raw_cap = 0;
     double* d_partial = nullptr;        // [maxb][max groups]
     size_t partial_cap = 0;
     // staging for the host entry points
@@ -232,6 +233,25 @@ int ensure_partial(lcu_model* m)
     m->d_partial = nullptr;
     RT_CHECK(cudaMalloc(&m->d_partial, need*sizeof(double)));
     m->partial_cap = need;
+    return LCU_OK;
+}
+
+// staging for the rendered (pre-PSF) images of up to nb points per launch
+int ensure_raw(lcu_model* m, size_t nb)
+{
+    if(!m->has_psf || nb <= m->raw_cap)
+        return LCU_OK;
+    if(m->graph1)
+    {
+        cudaGraphExecDestroy(m->graph1);    // the graph refers to the old buffer
+        m->graph1 = nullptr;
+    }
+    if(m->d_raw)
+        cudaFree(m->d_raw);
+    m->d_raw = nullptr;
+    m->raw_cap = 0;
+    RT_CHECK(cudaMalloc(&m->d_raw, nb*m->size*sizeof(float)));
+    m->raw_cap = nb;
     return LCU_OK;
 }
 
@@ -402,6 +422,8 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
 {
     int rc = ensure_partial(m);
     if(rc) return rc;
+    rc = ensure_raw(m, std::min(m->maxb, nbatch));
+    if(rc) return rc;
     const int ngroups = (int)group_count(m);
     for(size_t b0 = 0; b0 < nbatch; b0 += m->maxb)
     {
@@ -436,7 +458,7 @@ bool single_point_graph(lcu_model* m)
         cudaGraphExecDestroy(m->graph1);
         m->graph1 = nullptr;
     }
-    if(getenv("LCU_NO_GRAPH") || ensure_partial(m) != LCU_OK)
+    if(getenv("LCU_NO_GRAPH") || ensure_partial(m) != LCU_OK || ensure_raw(m, 1) != LCU_OK)
     {
         m->graph1_off = true;
         return false;
@@ -874,8 +896,6 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(RT_CHECK(cudaMemcpy(m->d_image, desc->image, m->size*sizeof(float), cudaMemcpyHostToDevice)));
     M_CHECK(RT_CHECK(cudaMemcpy(m->d_weight, desc->weight, m->size*sizeof(float), cudaMemcpyHostToDevice)));
     M_CHECK(RT_CHECK(cudaMalloc(&m->d_objs, m->maxb*m->words*sizeof(uint32_t))));
-    if(m->has_psf)
-        M_CHECK(RT_CHECK(cudaMalloc(&m->d_raw, m->maxb*m->size*sizeof(float))));
     for(cudaEvent_t& e : m->ev_io)
         M_CHECK(RT_CHECK(cudaEventCreate(&e)));
     M_CHECK(return ensure_partial(m));

@@ -375,3 +375,15 @@ def test_every_object_in_one_model(gpu_ctx, flags):
     got = m.loglike(params)
     assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew)          # 60^2 pixels
     _check_block(m, om, cfg)
+
+
+def test_pixel_coordinate_system(gpu_ctx):
+    """Image sections: origin and pixel scale (src/data.c:236-276) enter the
+    pixel positions (kernel/lensed.cl:24) and scale the quadrature abscissae
+    (src/quadrature.c:38-39)."""
+    w = H.workloads.c4(128)
+    img = np.zeros((48, 56), np.float32)
+    for pcs in ((33.0, 41.0, 1.0, 1.0), (20.0, 30.0, 2.0, 2.0), (20.5, 30.25, 1.5, -0.75)):
+        cfg = H.Config(f"pcs{pcs}", w["objects"], w["truth"], img, np.ones_like(img), rule="g3k7", psf=H.workloads.gaussian_psf(5, 5, 1.0), pcs=pcs)
+        om, m = cfg.oracle(), cfg.product(gpu_ctx)
+        _check_images(m.render(cfg.params), cfg, om)
