@@ -319,6 +319,12 @@ def build(path: str, ctx: Context, **model_kw):
         weight = (gain.astype(np.float64)/(image.astype(np.float64) + float(opt.get("offset", 0)))).astype(np.float32)
     if "xweight" in opt:
         weight = weight*value_or_file(opt["xweight"])
+    if "mask" in opt:
+        # FITS mask: non-zero pixels are excluded by zero weight (src/lensed.c:471-486)
+        mask, _ = fits.read_image(rel(opt["mask"]))
+        if mask.shape != image.shape:
+            raise ValueError(f"wrong dimensions {mask.shape[1]} x {mask.shape[0]} for mask")
+        weight = np.where(mask != 0, np.float32(0), weight).astype(np.float32)
     psf = None
     if "psf" in opt:
         psf, _ = fits.read_image(rel(opt["psf"]))
@@ -327,6 +333,33 @@ def build(path: str, ctx: Context, **model_kw):
     model = Model(ctx, [o.name for o in cfg.objects], image, weight, rule=opt.get("rule", "g3k7"), psf=psf, pcs=pcs,
                   ipp=ipp, **model_kw)
     return cfg, model, Likelihood(cfg, model)
+
+
+def find_mode(values, mask=None, bins: int = 100):
+    """Mode and FWHM of the pixel-value histogram, the reference's background
+    check (src/data.c:421-501; src/lensed.c:519-547 warns when |mode| exceeds
+    half the FWHM and there is no sky object)."""
+    v = np.asarray(values, np.float64).ravel()
+    if mask is not None:
+        v = v[np.asarray(mask).ravel() != 0]
+    if v.size == 0:
+        return float("nan"), 0.0
+    lo, hi = v.min(), v.max()
+    if lo == hi:
+        return float(lo), 0.0
+    dx = (hi - lo)/bins
+    j = np.minimum(((v - lo)/dx).astype(np.int64), bins - 1)
+    counts = np.bincount(j, minlength=bins)
+    peak = int(np.argmax(counts))                 # first of equal maxima, as the reference
+    mode = lo + (peak + 0.5)*dx
+    i = peak + 1
+    while i < bins and counts[i] >= 0.5*counts[peak]:
+        i += 1
+    fwhm = i*dx
+    i = peak
+    while i > 0 and counts[i - 1] >= 0.5*counts[peak]:
+        i -= 1
+    return float(mode), float(fwhm - (i - 1)*dx)
 
 
 # ---------------------------------------------------------------------------

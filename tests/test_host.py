@@ -140,3 +140,22 @@ def test_reference_style_known_answer_run(gpu_ctx, tmp_path):
     back = fits.read_hdus(str(tmp_path / "out.fits"))
     assert [h["EXTNAME"] for h, _ in back] == ["IMG", "RES", "RAW", "ERR", "WHT", "PVL"]
     assert np.array_equal(back[0][1], layers["IMG"])
+
+
+def test_find_mode_and_mask(compile_ctx, tmp_path):
+    rng = np.random.default_rng(0)
+    img = (0.3 + 0.05*rng.standard_normal((64, 64))).astype(np.float32)
+    img[:4, :4] = 50.0                                        # a bright source does not move the mode
+    mode, fwhm = host.find_mode(img, np.ones_like(img))
+    assert abs(mode - 0.3) < 0.3 and 0 < fwhm                 # 100 bins over [min, 50]: coarse, like the reference
+    mode, fwhm = host.find_mode(img[8:], None)
+    assert abs(mode - 0.3) < 0.02 and abs(fwhm - 2.355*0.05) < 0.05
+    assert host.find_mode(np.full(10, 2.0)) == (2.0, 0.0)
+    # mask option: masked pixels get zero weight
+    path = _write_case(tmp_path)
+    mask = np.zeros((40, 48), np.float32)
+    mask[5:9, 7:11] = 1
+    fits.write_layers(str(tmp_path / "mask.fits"), [mask], ["MASK"])
+    open(path, "w").write(INI.replace("rule   = g3k7", "rule   = g3k7\nmask   = mask.fits"))
+    cfg, model, like = host.build(path, compile_ctx)
+    assert model.npars == 22
