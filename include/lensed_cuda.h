@@ -132,7 +132,6 @@ typedef struct
 #define LCU_FAST_LENS_INTRINSICS 16u /* the same in LENS objects (less accurate deflections) */
 #define LCU_FAST_ATANH      32u /* atanh in LENS objects = (ln(1+x) - ln(1-x))/2 on the hardware
                                    log2: absolute error 2e-7 (isothermal ellipsoid deflections) */
-#define LCU_FAST_DIVSQRT    8u  /* approximate division and square root (2 ulp) */
 
 typedef struct
 {

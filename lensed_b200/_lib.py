@@ -83,7 +83,6 @@ SYMBOLS = {
 LCU_FAST_MATH = 1
 LCU_OBJ_SHARED = 2
 LCU_FAST_INTRINSICS = 4
-LCU_FAST_DIVSQRT = 8
 LCU_FAST_LENS_INTRINSICS = 16
 LCU_FAST_ATANH = 32
 

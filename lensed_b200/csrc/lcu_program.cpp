@@ -405,8 +405,7 @@ std::vector<lcu::Header> lcu_ctx::headers() const
 // level by shim.cuh; measured as accurate as the strict build on Sersic
 // scenes), LCU_FAST_LENS_INTRINSICS = the same in lens objects (costs accuracy
 // in the deflection), LCU_FAST_ATANH = atanh of lens objects on the hardware
-// log2 (absolute error 2e-7), LCU_FAST_DIVSQRT = approximate division and
-// square root.
+// log2 (absolute error 2e-7).  Division and square root are always IEEE.
 // Denormals are flushed either way.
 std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
 {
@@ -422,8 +421,8 @@ std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
     o.push_back((flags & LCU_FAST_ATANH) ? "-DLCU_ATANH_LENS=1" : "-DLCU_ATANH_LENS=0");
     o.push_back("-DLCU_ATANH_SOURCE=0");
     o.push_back("--ftz=true");
-    o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-div=false" : "--prec-div=true");
-    o.push_back((flags & LCU_FAST_DIVSQRT) ? "--prec-sqrt=false" : "--prec-sqrt=true");
+    o.push_back("--prec-div=true");
+    o.push_back("--prec-sqrt=true");
     o.push_back((flags & LCU_FAST_MATH) ? "--fmad=true" : "--fmad=false");
     const char* extra = getenv("LCU_NVRTC_FLAGS");
     if(extra && *extra)
