@@ -298,6 +298,7 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {'+'.join(w['objects'])}, {w['width']}x{w['height']}, PSF 25x25, rule {w['rule']}",
                        "points_per_gpu_per_step": B, "rays_per_eval": work["rays"], "parallelism": f"points x{world}",
+                       "rays_per_thread": model.rays_per_thread,
                        "math": "strict: IEEE ops in source order, accurate libdevice functions, no FMA contraction" if flags == 0 else
                                "LCU_FAST_INTRINSICS|LCU_FAST_ATANH: exp/log of source and foreground objects and atanh of lens objects "
                                "on the hardware exp2/log2 units; division, sqrt, atan, no FMA contraction and the summation order "
@@ -310,7 +311,7 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(P.nbytes), "d2h_bytes_per_step": int(8*B)},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "lcu_render_s1", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "kernel": "lcu_render_pair" if model.rays_per_thread == 2 else "lcu_render_s1", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved/fp32_peak if achieved and fp32_peak else None, "traffic": traffic,
                 "peak_source": "FFMA micro-benchmark run in this process (MEASURED_PEAKS.json records no FP32 peak)",
                 "algorithmic": f"{w['flops_per_ray']} flop + {w['transc_per_ray']} transcendental calls per ray x "

@@ -100,6 +100,14 @@ void lcu_destroy(lcu_ctx* ctx);
  */
 int lcu_object_info(lcu_ctx* ctx, const char* name, int* type, size_t* words,
                     size_t* npar, lcu_param* params, size_t cap);
+/*
+ * Can the object's per-ray function (deflection / brightness / foreground) be
+ * compiled for two rays per thread (packed FP32 arithmetic)?  Returns 1 or 0,
+ * or a negative error code if the object cannot be loaded; with 0, *why (if
+ * not NULL) points at the compiler's reason, valid until the context is
+ * destroyed.  No counterpart in the reference: a property of this back end.
+ */
+int lcu_object_pairable(lcu_ctx* ctx, const char* name, const char** why);
 
 /*
  * Quadrature rules, replaces QUAD_RULES[] and quad_rule()
@@ -129,6 +137,9 @@ typedef struct
                                 the constant bank */
 #define LCU_FAST_INTRINSICS 4u  /* exp/log/pow/sin/cos -> hardware exp2/log2/sin/cos
                                    approximations in SOURCE and FOREGROUND objects */
+#define LCU_NO_PAIR     8u   /* render one ray per thread even if every object can be
+                                compiled for two (packed FADD2/FMUL2/FFMA2 arithmetic);
+                                both ways give the same bits, this one is slower */
 #define LCU_FAST_LENS_INTRINSICS 16u /* the same in LENS objects (less accurate deflections) */
 #define LCU_FAST_ATANH      32u /* atanh in LENS objects = (ln(1+x) - ln(1-x))/2 on the hardware
                                    log2: absolute error 2e-7 (isothermal ellipsoid deflections) */
@@ -163,6 +174,9 @@ void lcu_model_destroy(lcu_model* model);
 size_t lcu_model_npars(const lcu_model* model);    /* total parameters, object order */
 size_t lcu_model_words(const lcu_model* model);    /* object block size in 4-byte words */
 size_t lcu_model_max_batch(const lcu_model* model);
+/* rays per thread of the render kernel for large images: 2 if every object is
+   pairable and LCU_NO_PAIR is not set, else 1 */
+int lcu_model_rays_per_thread(const lcu_model* model);
 /* assembled program text (what `output = true` dumps as <root>kernel.cl, src/lensed.c:714-735) */
 const char* lcu_model_source(const lcu_model* model);
 const char* lcu_model_build_log(const lcu_model* model);

@@ -56,6 +56,7 @@ SYMBOLS = {
     "lcu_destroy": (None, [C.c_void_p]),
     "lcu_object_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t),
                                   C.POINTER(C.c_size_t), C.POINTER(LcuParam), C.c_size_t]),
+    "lcu_object_pairable": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]),
     "lcu_quad_rule_count": (C.c_int, []),
     "lcu_quad_rule_name": (C.c_char_p, [C.c_int]),
     "lcu_quad_rule_info": (C.c_char_p, [C.c_int]),
@@ -66,6 +67,7 @@ SYMBOLS = {
     "lcu_model_npars": (C.c_size_t, [C.c_void_p]),
     "lcu_model_words": (C.c_size_t, [C.c_void_p]),
     "lcu_model_max_batch": (C.c_size_t, [C.c_void_p]),
+    "lcu_model_rays_per_thread": (C.c_int, [C.c_void_p]),
     "lcu_model_source": (C.c_char_p, [C.c_void_p]),
     "lcu_model_build_log": (C.c_char_p, [C.c_void_p]),
     "lcu_model_cubin": (C.c_size_t, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -83,6 +85,7 @@ SYMBOLS = {
 LCU_FAST_MATH = 1
 LCU_OBJ_SHARED = 2
 LCU_FAST_INTRINSICS = 4
+LCU_NO_PAIR = 8
 LCU_FAST_LENS_INTRINSICS = 16
 LCU_FAST_ATANH = 32
 

@@ -108,6 +108,15 @@ class Context:
                              d > 0 or bool(np.signbit(np.float32(d)))))
         return ObjectInfo(name, chr(t.value), int(w.value), out)
 
+    def object_pairable(self, name: str):
+        """(True, "") if the object's per-ray code compiles for two rays per
+        thread, else (False, compiler log)."""
+        why = C.c_char_p()
+        rc = lib.lcu_object_pairable(self._h, name.encode(), C.byref(why))
+        if rc < 0:
+            check(-rc)
+        return bool(rc), (why.value or b"").decode()
+
     def fp32_peak_tflops(self) -> float:
         v = C.c_double()
         check(lib.lcu_measure_fp32_peak(self._h, C.byref(v)))
@@ -178,6 +187,10 @@ class Model:
             self.close()
         except Exception:
             pass
+
+    @property
+    def rays_per_thread(self) -> int:
+        return int(lib.lcu_model_rays_per_thread(self._h))
 
     @property
     def source(self) -> str:

@@ -26,6 +26,8 @@ struct ObjectInfo
     size_t bytes = 0;       // sizeof(struct data_<ident>)
     size_t words = 0;       // 4-byte words, rounded up (src/input/objects.c:139)
     std::vector<lcu_param> params;
+    bool pairable = false;  // the per-ray functions also compile for two rays per thread (shim.cuh)
+    std::string pair_log;   // why not, if not
 };
 
 struct ModelObject
@@ -54,7 +56,8 @@ std::string wrap_object(const std::string& name, const std::string& ident, const
 
 // src/kernel.c:235-399 and :401-656 equivalents: CUDA text of
 // lcu_compute() and lcu_set_params_body() for an object list
-std::string generate_compute(const std::vector<ModelObject>& objs);
+std::string generate_compute(const std::vector<ModelObject>& objs, bool pair = false);
+std::string strip_for_pair(const std::string& text);
 std::string generate_set_params(const std::vector<ModelObject>& objs);
 
 // NVRTC: source (+ named headers) -> sm_100a cubin

@@ -75,6 +75,104 @@ std::string make_ident(const std::string& name)
     return id;
 }
 
+// The pair copy of an object (two rays per thread, shim.cuh) needs only the
+// functions that run per ray.  Everything that describes or fills the data
+// block -- `type = ...;`, `params {...};`, `data {...};` and the set() function
+// -- is blanked out of that copy (newlines kept, so that diagnostics still
+// point at the right line): the data block has one layout, defined by the
+// scalar copy, and set() may branch on its arguments, which pairs cannot.
+// A small scanner rather than a parser: top-level items end at a ';' or at the
+// '}' that closes a function body; comments, literals and preprocessor lines
+// are skipped over.
+std::string strip_for_pair(const std::string& text)
+{
+    std::string out = text;
+    const size_t n = text.size();
+    size_t item = 0;            // start of the current top-level item
+    int depth = 0;
+    bool body = false;          // the item has had a '{' ... '}' at depth 0
+    auto is_id = [](char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; };
+    // decide about the item [item, end) and start the next one
+    auto close = [&](size_t end)
+    {
+        // identifiers outside comments up to the first '{' or '='
+        std::vector<std::string> ids;
+        bool call_set = false;
+        for(size_t i = item; i < end; )
+        {
+            const char c = text[i];
+            if(c == '/' && i + 1 < end && text[i + 1] == '/') { while(i < end && text[i] != '\n') ++i; continue; }
+            if(c == '/' && i + 1 < end && text[i + 1] == '*') { i += 2; while(i + 1 < end && !(text[i] == '*' && text[i + 1] == '/')) ++i; i += 2; continue; }
+            if(c == '{' || c == '=') break;
+            if(is_id(c))
+            {
+                size_t j = i;
+                while(j < end && is_id(text[j])) ++j;
+                ids.push_back(text.substr(i, j - i));
+                size_t k = j;
+                while(k < end && (text[k] == ' ' || text[k] == '\t' || text[k] == '\n' || text[k] == '\r')) ++k;
+                if(ids.back() == "set" && k < end && text[k] == '(')
+                    call_set = true;
+                i = j;
+                if(c == '(') break;
+                continue;
+            }
+            if(c == '(') { break; }
+            ++i;
+        }
+        const bool drop = call_set || (!ids.empty() && (ids[0] == "type" || ids[0] == "params" || ids[0] == "data"));
+        if(drop)
+            for(size_t i = item; i < end; ++i)
+                if(out[i] != '\n')
+                    out[i] = ' ';
+        item = end;
+        body = false;
+    };
+    for(size_t i = 0; i < n; )
+    {
+        const char c = text[i];
+        if(c == '/' && i + 1 < n && text[i + 1] == '/') { while(i < n && text[i] != '\n') ++i; continue; }
+        if(c == '/' && i + 1 < n && text[i + 1] == '*') { i += 2; while(i + 1 < n && !(text[i] == '*' && text[i + 1] == '/')) ++i; i += 2; continue; }
+        if(c == '"' || c == '\'')
+        {
+            const char q = c;
+            ++i;
+            while(i < n && text[i] != q) { if(text[i] == '\\') ++i; ++i; }
+            ++i;
+            continue;
+        }
+        if(c == '#' && depth == 0)
+        {
+            // preprocessor line (with continuations): an item of its own, kept
+            size_t j = i;
+            while(j < n && text[j] != '\n') { if(text[j] == '\\' && j + 1 < n && text[j + 1] == '\n') ++j; ++j; }
+            item = j;
+            i = j;
+            continue;
+        }
+        if(c == '{') { ++depth; ++i; continue; }
+        if(c == '}')
+        {
+            --depth;
+            ++i;
+            if(depth == 0)
+                body = true;
+            continue;
+        }
+        if(depth == 0 && body && c != ' ' && c != '\t' && c != '\n' && c != '\r' && c != ';')
+        {
+            // something new starts after a closed body: it was a function
+            close(i);
+            continue;
+        }
+        if(c == ';' && depth == 0) { ++i; close(i); continue; }
+        ++i;
+    }
+    if(body)
+        close(n);
+    return out;
+}
+
 // The name-mangling wrapper of src/kernel.c:153-172 (OBJHEAD / OBJFOOT), plus
 // the metadata export that replaces the meta_<name> / params_<name> kernels
 // of src/kernel.c:41-62: type, sizeof(data) and the parameter count become an
@@ -129,6 +227,27 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "#define LCU_ACCURATE_OFF\n#include \"shim.cuh\"\n"
       << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
       << "} // namespace lcu_setter\n\n";
+    // Third copy, for the two-rays-per-thread render kernel: the per-ray
+    // functions with float = a packed pair (shim.cuh), the data block shared
+    // with the scalar copy.  Only compiled when every object of the model
+    // can be typed that way (LCU_PAIR, decided in lcu_ctx::object).
+    s << "#if LCU_PAIR\nnamespace lcu_pair {\n"
+      << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
+      << "#define LCU_PAIR_ON\n#include \"shim.cuh\"\n"
+      << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"
+      << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_ON\n#include \"shim.cuh\"\n#endif\n"
+      << "#define data struct ::data_" << id << "\n"
+      << "#define deflection deflection_" << id << "\n"
+      << "#define brightness brightness_" << id << "\n"
+      << "#define foreground foreground_" << id << "\n"
+      << "#line 1 \"objects/" << name << ".cl\"\n"
+      << rewrite_literals(strip_for_pair(text)) << "\n"
+      << "#undef data\n#undef deflection\n#undef brightness\n#undef foreground\n"
+      << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_OFF\n#include \"shim.cuh\"\n#endif\n"
+      << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_OFF\n#include \"shim.cuh\"\n#endif\n"
+      << "#define LCU_PAIR_OFF\n#include \"shim.cuh\"\n"
+      << "#define LCU_SHIM_OFF\n#include \"shim.cuh\"\n"
+      << "} // namespace lcu_pair\n#endif\n\n";
     return s.str();
 }
 
@@ -143,12 +262,17 @@ static const char* DEFLECT =
 // from LENS closes the lens plane: the summed deflection is applied to the
 // ray if finite.  Sources see the ray position y, foregrounds the image-plane
 // position x.
-std::string generate_compute(const std::vector<ModelObject>& objs)
+std::string generate_compute(const std::vector<ModelObject>& objs, bool pair)
 {
+    // pair: the same function for two rays per thread, on the lcu_pair copies
+    // of the objects (lcu_compute2, shim.cuh: packed pairs)
+    const char* V2 = pair ? "lcu_pf2" : "lcu_float2";
+    const char* NS = pair ? "lcu_pair::" : "";
+    const std::string DEFLECT = pair ? " -= lcu_pair_guard(a);\n" : lcu::DEFLECT;
     std::ostringstream s;
-    s << "__device__ __forceinline__ float lcu_compute(const uint* data, lcu_float2 x)\n{\n"
-      << "    lcu_float2 y = x;\n"
-      << "    float f = 0;\n";
+    s << "__device__ __forceinline__ " << (pair ? "lcu_pf lcu_compute2" : "float lcu_compute") << "(const uint* data, " << V2 << " x)\n{\n"
+      << "    " << V2 << " y = x;\n"
+      << "    " << (pair ? "lcu_pf" : "float") << " f = 0;\n";
     int type = 0, trigger = 0;
     bool open = false;
     // The reference starts every sum from zero ("float2 a = 0; a += ...",
@@ -173,7 +297,7 @@ std::string generate_compute(const std::vector<ModelObject>& objs)
         {
             if(t == LCU_LENS && !open)
             {
-                s << "    {\n        lcu_float2 a;\n";
+                s << "    {\n        " << V2 << " a;\n";
                 open = true;
                 first_lens = true;
             }
@@ -182,12 +306,12 @@ std::string generate_compute(const std::vector<ModelObject>& objs)
         const char* ind = open ? "        " : "    ";
         if(t == LCU_LENS)
         {
-            s << ind << (first_lens ? "a = " : "a += ") << "deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+            s << ind << (first_lens ? "a = " : "a += ") << NS << "deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
             first_lens = false;
         }
         else
         {
-            s << ind << (first_light ? "f = " : "f += ") << (t == LCU_SOURCE ? "brightness_" : "foreground_") << id
+            s << ind << (first_light ? "f = " : "f += ") << NS << (t == LCU_SOURCE ? "brightness_" : "foreground_") << id
               << "((struct data_" << id << "*)(data + " << o.d << "), " << (t == LCU_SOURCE ? "y" : "x") << ");\n";
             first_light = false;
         }
@@ -424,6 +548,7 @@ std::vector<std::string> lcu_ctx::build_options(unsigned flags) const
     o.push_back("--prec-div=true");
     o.push_back("--prec-sqrt=true");
     o.push_back((flags & LCU_FAST_MATH) ? "--fmad=true" : "--fmad=false");
+    o.push_back((flags & LCU_FAST_MATH) ? "-DLCU_FMAD=1" : "-DLCU_FMAD=0");
     const char* extra = getenv("LCU_NVRTC_FLAGS");
     if(extra && *extra)
     {
@@ -496,12 +621,20 @@ const lcu::ObjectInfo* lcu_ctx::object(const std::string& name)
         src += w;
     }
 
+    // first with the two-rays-per-thread copy of the per-ray functions; an
+    // object whose text cannot be typed as pairs is not an error, it renders
+    // one ray per thread
     std::vector<char> cubin;
     std::string log;
-    if(!compile_cubin(src, headers(), build_options(0), &cubin, &log))
+    info.pairable = compile_cubin("#define LCU_PAIR 1\n" + src, headers(), build_options(0), &cubin, &log);
+    if(!info.pairable)
     {
-        set_error("object %s: failed to build program\n%s", name.c_str(), log.c_str());
-        return nullptr;
+        info.pair_log = log;
+        if(!compile_cubin("#define LCU_PAIR 0\n" + src, headers(), build_options(0), &cubin, &log))
+        {
+            set_error("object %s: failed to build program\n%s", name.c_str(), log.c_str());
+            return nullptr;
+        }
     }
 
     const unsigned char* bytes = nullptr;

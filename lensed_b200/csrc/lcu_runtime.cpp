@@ -158,6 +158,8 @@ struct lcu_model
     // device state
     CUmodule mod = nullptr;
     CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_reduce = nullptr;
+    CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
+    bool pair = false;
     CUdeviceptr c_objs = 0;
     cudaStream_t stream = nullptr;
     float *d_image = nullptr, *d_weight = nullptr;
@@ -346,9 +348,14 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         }
         const int split = pick_split(m, nk, nb);
         const int idx = split == 1 ? 0 : split == 2 ? 1 : split == 4 ? 2 : 3;
-        const size_t ppb = 256/split;
         void* args[] = { &a };
-        int rc = launch(m, a.error ? m->f_render_err[idx] : m->f_render[idx], dim3((unsigned)div_up(nk, ppb), (unsigned)nb),
+        int rc;
+        if(split == 1 && m->pair)
+            // two pixels per thread: 512 per block
+            rc = launch(m, a.error ? m->f_render_pair_err : m->f_render_pair, dim3((unsigned)div_up(nk, 512), (unsigned)nb),
+                        dim3(256), args, st);
+        else
+            rc = launch(m, a.error ? m->f_render_err[idx] : m->f_render[idx], dim3((unsigned)div_up(nk, 256/split), (unsigned)nb),
                         dim3(256), args, st);
         if(rc) return rc;
     }
@@ -594,6 +601,21 @@ int lcu_create(int device, const char* kernel_dir, const char* objects_dir, lcu_
 
 void lcu_destroy(lcu_ctx* ctx) { delete ctx; }
 
+int lcu_object_pairable(lcu_ctx* ctx, const char* name, const char** why)
+{
+    if(!ctx || !name)
+    {
+        set_error("lcu_object_pairable: null argument");
+        return -LCU_E_ARG;
+    }
+    const ObjectInfo* info = ctx->object(name);
+    if(!info)
+        return -LCU_E_COMPILE;
+    if(why)
+        *why = info->pair_log.c_str();
+    return info->pairable ? 1 : 0;
+}
+
 int lcu_object_info(lcu_ctx* ctx, const char* name, int* type, size_t* words, size_t* npar,
                     lcu_param* params, size_t cap)
 {
@@ -732,6 +754,15 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     m->psfh = m->has_psf ? desc->psf_height : 0;
     m->flags = desc->flags;
     m->obj_const = !(desc->flags & LCU_OBJ_SHARED);
+    // two rays per thread if every object's per-ray code can be typed as pairs
+    m->pair = !(desc->flags & LCU_NO_PAIR);
+    for(const ModelObject& o : m->objs)
+        m->pair = m->pair && o.info->pairable;
+    {
+        const char* env = getenv("LCU_PAIR");
+        if(env && *env == '0')
+            m->pair = false;
+    }
 
     if(m->has_psf)
     {
@@ -809,6 +840,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "#define LCU_NPARS " << std::max<size_t>(m->npars, 1) << "\n"
           << "#define LCU_MAXB " << m->maxb << "\n"
           << "#define LCU_OBJ_CONST " << (m->obj_const ? 1 : 0) << "\n"
+          << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n"
           << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
         std::vector<const ObjectInfo*> uniq;
         for(const ModelObject& o : m->objs)
@@ -820,6 +852,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "// compute\n"
           << "//----------------------------------------------------------------------------\n"
           << generate_compute(m->objs)
+          << (m->pair ? generate_compute(m->objs, true) : std::string())
           << "//----------------------------------------------------------------------------\n"
           << "// set_params\n"
           << "//----------------------------------------------------------------------------\n"
@@ -861,6 +894,11 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[1], m->mod, "lcu_render_err_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[2], m->mod, "lcu_render_err_s4")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[3], m->mod, "lcu_render_err_s8")));
+    if(m->pair)
+    {
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair, m->mod, "lcu_render_pair")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair_err, m->mod, "lcu_render_pair_err")));
+    }
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
     if(m->has_psf)
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv, m->mod, "lcu_convolve")));
@@ -917,6 +955,7 @@ void lcu_model_destroy(lcu_model* m)
 size_t lcu_model_npars(const lcu_model* m) { return m ? m->npars : 0; }
 size_t lcu_model_words(const lcu_model* m) { return m ? m->words : 0; }
 size_t lcu_model_max_batch(const lcu_model* m) { return m ? m->maxb : 0; }
+int lcu_model_rays_per_thread(const lcu_model* m) { return m ? (m->pair ? 2 : 1) : 0; }
 const char* lcu_model_source(const lcu_model* m) { return m ? m->source.c_str() : nullptr; }
 const char* lcu_model_build_log(const lcu_model* m) { return m ? m->log.c_str() : nullptr; }
 

@@ -250,6 +250,124 @@ LCU_RENDER_KERNEL(2)
 LCU_RENDER_KERNEL(4)
 LCU_RENDER_KERNEL(8)
 
+#if LCU_PAIR
+// Two rays per thread (shim.cuh: packed pairs).  A warp covers 64 consecutive
+// pixels: lane l shoots the rays of pixels l and 32 + l through
+// lcu_compute2(), whose adds and multiplies are FADD2 / FMUL2 / FFMA2 -- half
+// the FP32 instructions per ray of the one-ray kernel.  Per pixel the arithmetic
+// and its order are those of lcu_render_s1, and each half of the warp is one
+// 32-pixel group of the chi^2 partial sums with the same lane layout, so the
+// outputs are the same bits.
+template<bool ERR>
+__device__ __forceinline__ void lcu_render_pair_impl(const lcu_render_args& a)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+
+    const long long kk0 = (long long)blockIdx.x*(2*LCU_BLOCK) + warp*64 + lane;
+    const long long kk1 = kk0 + 32;
+    const bool live0 = kk0 < a.nk, live1 = kk1 < a.nk;
+    const long long k0 = a.k0 + (live0 ? kk0 : 0);
+    const long long k1 = a.k0 + (live1 ? kk1 : 0);
+
+#if LCU_OBJ_CONST
+    const uint* data = reinterpret_cast<const uint*>(lcu_objs_c) + b*LCU_WORDS;
+#else
+    __shared__ __align__(16) uint sdata[LCU_WORDS];
+    for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+        sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
+    __syncthreads();
+    const uint* data = sdata;
+#endif
+
+    // pixel positions, kernel/lensed.cl:24
+    const lcu_pf px((float)(k0 % IMAGE_WIDTH), (float)(k1 % IMAGE_WIDTH));
+    const lcu_pf py((float)(k0 / IMAGE_WIDTH), (float)(k1 / IMAGE_WIDTH));
+    const lcu_pf2 x(lcu_pf(a.pcs.x) + lcu_pf(a.pcs.z)*px, lcu_pf(a.pcs.y) + lcu_pf(a.pcs.w)*py);
+
+    // value and error of quadrature, kernel/lensed.cl:27-32
+    lcu_pf f0 = 0.0f, f1 = 0.0f;
+    if(live0)
+    {
+#if LCU_QUAD_NI > 0
+#pragma unroll 1
+        for(int i = 0; i < LCU_QUAD_NI; ++i)
+        {
+            const lcu_pf rx = x.x + lcu_pf(lcu_quad[i*LCU_QUAD_NJ].x);
+#pragma unroll 1
+            for(int j = 0; j < LCU_QUAD_NJ; ++j)
+            {
+                const float4 q = lcu_quad[i*LCU_QUAD_NJ + j];
+                const lcu_pf c = lcu_compute2(data, lcu_pf2(rx, x.y + lcu_pf(q.y)));
+                f0 = f0 + lcu_pf(q.z)*c;
+                if(ERR)
+                    f1 = f1 + lcu_pf(q.w)*c;
+            }
+        }
+#else
+#pragma unroll 1
+        for(int n = 0; n < QUAD_POINTS; ++n)
+        {
+            const float4 q = lcu_quad[n];
+            const lcu_pf c = lcu_compute2(data, lcu_pf2(x.x + lcu_pf(q.x), x.y + lcu_pf(q.y)));
+            f0 = f0 + lcu_pf(q.z)*c;
+            if(ERR)
+                f1 = f1 + lcu_pf(q.w)*c;
+        }
+#endif
+    }
+
+    // outputs and the fused loglike kernel, as in lcu_render_impl
+    const long long kk[2] = { kk0, kk1 };
+    const long long k[2] = { k0, k1 };
+    const bool live[2] = { live0, live1 };
+    const float v0[2] = { f0.lo(), f0.hi() };
+    const float v1[2] = { f1.lo(), f1.hi() };
+#pragma unroll
+    for(int h = 0; h < 2; ++h)
+    {
+        const size_t o = (size_t)b*IMAGE_SIZE + k[h];
+        float chi = 0;
+        if(live[h])
+        {
+            if(a.mode & LCU_OUT_VALUE)
+                a.value[o] = v0[h];
+            if(ERR && (a.mode & LCU_OUT_ERROR))
+                a.error[o] = v1[h];
+            if(a.mode & (LCU_OUT_CHI2 | LCU_OUT_CHIMAP))
+            {
+                const float d = __fadd_rn(v0[h], -a.image[k[h]]);
+                chi = __fmul_rn(__fmul_rn(a.weight[k[h]], d), d);
+                if(a.mode & LCU_OUT_CHIMAP)
+                    a.chimap[o] = chi;
+            }
+        }
+        if(a.mode & LCU_OUT_CHI2)
+        {
+            double s = chi;
+#pragma unroll
+            for(int off = 16; off > 0; off >>= 1)
+                s += __shfl_down_sync(0xffffffffu, s, off);
+            const long long g = (kk[h] - lane) >> 5;
+            if(lane == 0 && g < a.ngroups)
+                a.partial[(size_t)b*a.ngroups + g] = s;
+        }
+    }
+}
+
+// 3 resident blocks (<= 80 registers): with two rays per thread the kernel is
+// bound by the FP32 pipe, which a packed instruction occupies for two cycles;
+// 24 warps per SM keep it ~77 % busy, 16 warps ~73 % (profiles/)
+#ifndef LCU_PAIR_MINBLOCKS
+#define LCU_PAIR_MINBLOCKS 3
+#endif
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_PAIR_MINBLOCKS)
+lcu_render_pair(const __grid_constant__ lcu_render_args a) { lcu_render_pair_impl<false>(a); }
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_PAIR_MINBLOCKS)
+lcu_render_pair_err(const __grid_constant__ lcu_render_args a) { lcu_render_pair_impl<true>(a); }
+#endif // LCU_PAIR
+
 // ---------------------------------------------------------------------------
 // convolve + chi^2
 // ---------------------------------------------------------------------------

@@ -48,3 +48,14 @@ __device__ __forceinline__ lcu_float2 mv22(mat22 m, lcu_float2 v)
 {
     return lcu_float2(dot(m.lo, v), dot(m.hi, v));
 }
+
+// the same for two rays at once (shim.cuh: packed pairs); the matrix is either
+// a field of the object's data block (uniform) or a local of the plugin
+__device__ __forceinline__ lcu_pf2 mv22(lcu_pf4 m, lcu_pf2 v)
+{
+    return lcu_pf2(dot(m.lo, v), dot(m.hi, v));
+}
+__device__ __forceinline__ lcu_pf2 mv22(lcu_float4 m, lcu_pf2 v)
+{
+    return lcu_pf2(lcu_pf(m.x)*v.x + lcu_pf(m.y)*v.y, lcu_pf(m.z)*v.x + lcu_pf(m.w)*v.y);
+}

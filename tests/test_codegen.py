@@ -1,5 +1,6 @@
 """Generated lcu_compute() / lcu_set_params_body(): object order is the
 physics."""
+import os
 import re
 
 import numpy as np
@@ -52,3 +53,67 @@ def test_build_options_are_the_reference_macro_names(compile_ctx):
     for line in ("#define IMAGE_SIZE 35", "#define IMAGE_WIDTH 7", "#define IMAGE_HEIGHT 5", "#define PSF 1",
                  "#define PSF_WIDTH 4", "#define PSF_HEIGHT 3", "#define QUAD_POINTS 16"):
         assert line in m.source
+
+
+def test_pair_copy_of_every_shipped_object(compile_ctx):
+    """Every shipped object's per-ray function also compiles with float = a
+    packed pair of rays (shim.cuh); the model then carries lcu_compute2 and the
+    two-rays-per-thread kernels, unless LCU_NO_PAIR asks for one ray."""
+    import os
+    names = sorted(f[:-3] for f in os.listdir(os.path.join(os.path.dirname(L.__file__), "objects")) if f.endswith(".cl"))
+    assert len(names) == 15
+    for n in names:
+        ok, why = compile_ctx.object_pairable(n)
+        assert ok, f"{n}: {why}"
+    m = L.Model(compile_ctx, ["sie_plus_shear", "sersic", "sky"], IMG, IMG)
+    assert m.rays_per_thread == 2
+    assert "lcu_pf lcu_compute2(const uint* data, lcu_pf2 x)" in m.source
+    assert "a = lcu_pair::deflection_sie_plus_shear((struct data_sie_plus_shear*)(data + 0), y);" in m.source
+    assert "y -= lcu_pair_guard(a);" in m.source
+    m1 = L.Model(compile_ctx, ["sie_plus_shear", "sersic", "sky"], IMG, IMG, flags=L.LCU_NO_PAIR)
+    assert m1.rays_per_thread == 1 and "lcu_pf lcu_compute2(" not in m1.source
+
+
+def test_pair_copy_keeps_only_per_ray_code(compile_ctx):
+    """type / params / data / set() are blanked out of the pair copy (line
+    numbers preserved); helper functions and the per-ray function stay."""
+    m = L.Model(compile_ctx, ["sersic"], IMG, IMG)
+    src = m.source
+    pair = src[src.index("namespace lcu_pair {"):src.index("} // namespace lcu_pair")]
+    assert "brightness(" in pair and "tgamma" not in pair and "POSITION_X" not in pair and "half_inv_n;" not in pair
+    scalar = src[src.index('#line 1 "objects/sersic.cl"'):src.index("namespace lcu_setter")]
+    body = pair[pair.index('#line 1 "objects/sersic.cl"'):]
+    # same number of lines up to the per-ray function: diagnostics point at the right place
+    assert body[:body.index("brightness(")].count("\n") == scalar[:scalar.index("brightness(")].count("\n")
+
+
+def test_object_that_cannot_be_paired_falls_back(tmp_path):
+    """Branches on ray values, double arithmetic or integer casts cannot be
+    typed as pairs: such an object is not an error, the model renders one ray
+    per thread."""
+    import shutil
+    objdir = tmp_path / "objects"
+    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    (objdir / "ring.cl").write_text(
+        "type = SOURCE;\n"
+        "params { {\"x\", POSITION_X}, {\"y\", POSITION_Y}, {\"r\", RADIUS} };\n"
+        "data { float2 c; float r; };\n"
+        "static float brightness(local data* this, float2 x)\n"
+        "{\n    float d = length(x - this->c);\n    if(d < this->r)\n        return 1.0f;\n    return d > 2*this->r ? 0.0f : 0.5f;\n}\n"
+        "static void set(local data* this, float x, float y, float r)\n{\n    this->c = (float2)(x, y);\n    this->r = r;\n}\n")
+    (objdir / "dbl.cl").write_text(
+        "type = FOREGROUND;\nparams { {\"a\"} };\ndata { float a; };\n"
+        "static float foreground(local data* this, float2 x)\n{\n    return this->a*0.5*x.x;\n}\n"
+        "static void set(local data* this, float a)\n{\n    this->a = a;\n}\n")
+    ctx = L.Context(device=-1, objects_dir=str(objdir))
+    try:
+        ok, why = ctx.object_pairable("ring")
+        assert not ok and "ring.cl" in why
+        ok, why = ctx.object_pairable("dbl")
+        assert not ok
+        assert ctx.object_pairable("sie")[0]
+        m = L.Model(ctx, ["sie", "ring", "sky"], IMG, IMG)
+        assert m.rays_per_thread == 1 and "lcu_pf lcu_compute2(" not in m.source
+        assert L.Model(ctx, ["sie", "sersic", "sky"], IMG, IMG).rays_per_thread == 2
+    finally:
+        ctx.close()

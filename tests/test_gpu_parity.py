@@ -387,3 +387,65 @@ def test_pixel_coordinate_system(gpu_ctx):
         cfg = H.Config(f"pcs{pcs}", w["objects"], w["truth"], img, np.ones_like(img), rule="g3k7", psf=H.workloads.gaussian_psf(5, 5, 1.0), pcs=pcs)
         om, m = cfg.oracle(), cfg.product(gpu_ctx)
         _check_images(m.render(cfg.params), cfg, om)
+
+
+def _pair_cases():
+    cases = [("golden", n) for n in H.golden_names()]
+    cases += [("example", "test_sersic_bulge"), ("example", "full_mock_psf")]
+    cases += [("synthetic", ("c4", 160, True)), ("synthetic", ("c5", 96, True)), ("synthetic", ("c4", 75, False))]
+    return cases
+
+
+@pytest.mark.parametrize("flags", MATH_MODES)
+def test_two_rays_per_thread_same_bits(gpu_ctx, monkeypatch, flags):
+    """The packed two-rays-per-thread render kernel (FADD2 / FMUL2 / FFMA2,
+    shim.cuh) against the one-ray kernel on every shipped object: value and
+    error images, convolved model, chi^2 map and log-likelihood are the same
+    bits.  LCU_SPLIT=1 makes both models take their large-image kernel at
+    these test sizes; odd pixel counts cover the dead-lane tail."""
+    import lensed_b200 as L
+    monkeypatch.setenv("LCU_SPLIT", "1")
+    for kind, arg in _pair_cases():
+        cfg = H.golden_config(arg) if kind == "golden" else H.example_config(arg) if kind == "example" \
+            else H.synthetic_config(*arg[:2], psf=arg[2])
+        m2 = cfg.product(gpu_ctx, flags=flags)
+        m1 = cfg.product(gpu_ctx, flags=flags | L.LCU_NO_PAIR)
+        assert m2.rays_per_thread == 2 and m1.rays_per_thread == 1, cfg.name
+        a, b = m2.render(cfg.params), m1.render(cfg.params)
+        for key in ("raw", "error", "model", "chi"):
+            if a.get(key) is None:
+                continue
+            same = a[key].view(np.uint32) == b[key].view(np.uint32)
+            assert same.all(), f"{cfg.name}: {key} differs in {np.count_nonzero(~same)} pixels, first {np.argwhere(~same)[0]}"
+        assert m2.loglike(cfg.params) == m1.loglike(cfg.params), cfg.name
+        if kind == "synthetic":
+            P = H.workloads.param_batch(cfg.extra["workload"], 6)
+            assert np.array_equal(m2.loglike_batch(P), m1.loglike_batch(P)), cfg.name
+
+
+def test_two_rays_per_thread_guard_and_zoo(gpu_ctx, monkeypatch):
+    """Non-finite deflections (per-lane guard) and a nine-object model."""
+    import lensed_b200 as L
+    monkeypatch.setenv("LCU_SPLIT", "1")
+    img = np.zeros((9, 9), np.float32)
+    for lens, lp in (("sis", [5.0, 5.0, 2.0]), ("point_mass", [5.0, 5.0, 2.0]), ("nsis", [5.0, 5.0, 2.0, 0.0])):
+        params = np.array(lp + [5.0, 5.0, 1.5, -2.0, 1.0, 0.9, 10.0] + [0.25, 0.0, 0.0], np.float32)
+        cfg = H.Config("guard-" + lens, [lens, "sersic", "sky"], params, img, np.ones_like(img), rule="point")
+        a = cfg.product(gpu_ctx).render(params)
+        b = cfg.product(gpu_ctx, flags=L.LCU_NO_PAIR).render(params)
+        assert np.isfinite(a["raw"]).all()
+        assert np.array_equal(a["raw"].view(np.uint32), b["raw"].view(np.uint32)), lens
+    objects = ["sersic", "sky", "sie", "point_mass", "nsis", "epl", "sis_plus_shear", "nsie",
+               "gauss", "devauc", "exponential", "sersic-old"]
+    params = np.array(
+        [30.5, 30.5, 6.0, -4.0, 2.5, 0.8, 20.0, 0.02, 1e-4, -2e-4, 30.5, 30.5, 12.0, 0.7, 60.0, 38.0, 27.0, 2.0,
+         25.0, 35.0, 3.0, 1.5, 20.0, 40.0, 4.0, 1.2, 0.8, 10.0, 41.0, 42.0, 3.0, 0.05, -0.03, 15.0, 18.0, 2.5, 0.5, 0.6, 130.0,
+         44.0, 30.0, 1.5, -3.0, 0.9, 15.0, 31.0, 32.0, 2.0, -3.5, 0.7, 100.0,
+         29.0, 30.0, 1.0, -2.5, 0.6, 45.0, 32.0, 29.0, 1.5, -3.0, 1.2, 0.85, 70.0], np.float32)
+    img = np.zeros((61, 53), np.float32)
+    cfg = H.Config("zoo2", objects, params, img, np.ones_like(img), rule="gm75", psf=H.workloads.gaussian_psf(4, 5, 1.2))
+    m2, m1 = cfg.product(gpu_ctx), cfg.product(gpu_ctx, flags=L.LCU_NO_PAIR)
+    assert m2.npars == params.size and m2.rays_per_thread == 2
+    a, b = m2.render(params), m1.render(params)
+    for key in ("raw", "error", "model", "chi"):
+        assert np.array_equal(a[key].view(np.uint32), b[key].view(np.uint32)), key
