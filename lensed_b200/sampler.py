@@ -1,0 +1,353 @@
+"""Batch-native nested sampling on top of the batched likelihood entry point.
+
+The reference hands the evaluation of one parameter point at a time to
+MultiNest (``run()`` call in src/lensed.c:1236-1288, callback ``loglike`` in
+src/nested.c:17-131); MultiNest (a third-party Fortran library, "version 3.8
+or later", docs/dependencies.md:6, absent here) draws one point, waits for its
+likelihood, draws the next.  A GPU wants the opposite: ``lcu_loglike_batch``
+evaluates B points per launch (include/lensed_cuda.h).  This module is the
+driver that produces such batches: the nested
+sampling algorithm of Skilling (2004) with MultiNest's ellipsoidal rejection
+scheme (Feroz & Hobson 2008, the single-ellipsoid case, optionally split in
+two by k-means when that shrinks the volume), restated so that the B candidate
+points of one step are drawn *before* any of them is evaluated:
+
+    bound   = enlarged ellipsoid around the live points (intersected with the
+              unit cube)
+    cand    = B points uniform in bound                    -> one batched launch
+    for c in cand, in the order drawn:
+        if L(c) > L_min(live): the worst live point dies (weight L_min dX),
+                               c takes its place, X shrinks by exp(-1/nlive)
+
+Every candidate is an independent uniform draw from a region that contains the
+whole iso-likelihood contour of every threshold met during the step (contours
+only shrink), so a candidate accepted against the threshold current at its turn
+is a uniform draw from inside that contour -- the property nested sampling
+needs.  Nothing depends on the evaluation order inside the launch.
+
+Conventions follow MultiNest where Lensed exposes them
+(src/input/options.c:148-232, passed on in src/lensed.c:1248-1275): ``nlive``
+(default 300), ``tol`` (tolerance in log-evidence, 0.1), ``eff`` (MultiNest's
+efr, from ``shf`` = 0.8: the bound's volume is enlarged by 1/eff), ``seed``,
+``maxiter`` (0 = no limit).
+Outputs are in physical parameters, as the reference's callback overwrites the
+cube with them (src/nested.c:43-61); ``write_multinest`` writes the
+``<root>.txt`` / ``<root>post_equal_weights.dat`` / ``<root>stats.dat`` files in
+MultiNest's column layout.
+
+Host-side numpy only; all device work goes through the likelihood callable.
+With one process per GPU every rank runs the same sampler with the same seed
+and evaluates its slice of each batch (lensed_b200.distributed).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+
+@dataclass
+class NestedResult:
+    logz: float                     # ln evidence
+    logz_err: float                 # sqrt(H / nlive)
+    information: float              # H, nats
+    samples: np.ndarray             # [n][ndims] unit-cube positions, dead points then final live points
+    physical: Optional[np.ndarray]  # [n][npars] physical parameters (if a transform was given)
+    loglike: np.ndarray             # [n]
+    logwt: np.ndarray               # [n] ln posterior weight (normalised: logsumexp = 0)
+    niter: int                      # dead points
+    nevals: int                     # likelihood evaluations
+    nbatches: int                   # batched launches
+    efficiency: float               # accepted / evaluated after the initial live points
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def weights(self) -> np.ndarray:
+        return np.exp(self.logwt)
+
+    def mean(self, physical: bool = True) -> np.ndarray:
+        x = self.physical if physical and self.physical is not None else self.samples
+        return self.weights @ x
+
+    def std(self, physical: bool = True) -> np.ndarray:
+        x = self.physical if physical and self.physical is not None else self.samples
+        m = self.weights @ x
+        return np.sqrt(np.maximum(self.weights @ (x - m)**2, 0.0))
+
+    def max_like(self, physical: bool = True) -> np.ndarray:
+        x = self.physical if physical and self.physical is not None else self.samples
+        return x[int(np.argmax(self.loglike))]
+
+    def equal_weights(self, rng=None) -> np.ndarray:
+        """Indices of an equally weighted posterior sample (MultiNest's
+        post_equal_weights): point i is kept with probability w_i / max w."""
+        rng = np.random.default_rng(rng)
+        w = self.weights
+        return np.nonzero(rng.random(w.size) < w/w.max())[0]
+
+
+def _logaddexp(a: float, b: float) -> float:
+    if a == -math.inf:
+        return b
+    if b == -math.inf:
+        return a
+    m = max(a, b)
+    return m + math.log(math.exp(a - m) + math.exp(b - m))
+
+
+class _Ellipsoid:
+    """{u : (u - c)^T A^-1 (u - c) <= 1} around a set of points, enlarged so that
+    its volume is `enlarge` times that of the smallest similar ellipsoid
+    containing them all."""
+
+    def __init__(self, pts: np.ndarray, enlarge: float):
+        n, d = pts.shape
+        self.d = d
+        self.c = pts.mean(axis=0)
+        dx = pts - self.c
+        cov = dx.T @ dx/max(n - 1, 1)
+        # regularise degenerate directions (n <= d, or points on a hyperplane)
+        w, v = np.linalg.eigh(cov)
+        w = np.maximum(w, max(w.max(), 1e-300)*1e-12)
+        cov = (v*w) @ v.T
+        inv = (v/w) @ v.T
+        k = float(np.einsum("ij,jk,ik->i", dx, inv, dx).max())       # largest Mahalanobis distance^2
+        k = max(k, 1e-300)*enlarge**(2.0/d)
+        self.L = np.linalg.cholesky(cov*k)                            # A = L L^T
+        self.logvol = float(np.log(np.diag(self.L)).sum()) + _log_unit_ball(d)
+
+    def draw(self, n: int, rng) -> np.ndarray:
+        z = rng.standard_normal((n, self.d))
+        z /= np.linalg.norm(z, axis=1, keepdims=True)
+        r = rng.random(n)**(1.0/self.d)
+        return self.c + (z*r[:, None]) @ self.L.T
+
+    def contains(self, u: np.ndarray) -> np.ndarray:
+        y = np.linalg.solve(self.L, (u - self.c).T)
+        return (y*y).sum(axis=0) <= 1.0
+
+
+def _log_unit_ball(d: int) -> float:
+    return 0.5*d*math.log(math.pi) - math.lgamma(0.5*d + 1.0)
+
+
+def _kmeans2(pts: np.ndarray, rng, iters: int = 20):
+    """Two-means split of the live points (MultiNest partitions the live set
+    recursively this way); returns a boolean label array or None."""
+    n = pts.shape[0]
+    i = int(rng.integers(n))
+    j = int(np.argmax(((pts - pts[i])**2).sum(axis=1)))
+    c = np.stack([pts[i], pts[j]])
+    lab = None
+    for _ in range(iters):
+        d2 = ((pts[:, None, :] - c[None, :, :])**2).sum(axis=2)
+        new = d2[:, 1] < d2[:, 0]
+        if lab is not None and np.array_equal(new, lab):
+            break
+        lab = new
+        if lab.all() or not lab.any():
+            return None
+        c = np.stack([pts[~lab].mean(axis=0), pts[lab].mean(axis=0)])
+    return lab
+
+
+class _Bound:
+    """Union of one or two ellipsoids, intersected with the unit cube.  Uniform
+    sampling from a union: pick an ellipsoid by volume, draw, and accept with
+    probability 1 / (number of ellipsoids containing the point)."""
+
+    def __init__(self, pts: np.ndarray, enlarge: float, rng, split: bool):
+        d = pts.shape[1]
+        one = _Ellipsoid(pts, enlarge)
+        self.ells = [one]
+        if split and pts.shape[0] >= 4*(d + 1):
+            lab = _kmeans2(pts, rng)
+            if lab is not None and min(lab.sum(), (~lab).sum()) >= 2*(d + 1):
+                a, b = _Ellipsoid(pts[~lab], enlarge), _Ellipsoid(pts[lab], enlarge)
+                # split only if it pays clearly (MultiNest: total volume shrinks)
+                if np.logaddexp(a.logvol, b.logvol) < one.logvol + math.log(0.5):
+                    self.ells = [a, b]
+        lv = np.array([e.logvol for e in self.ells])
+        self.logvol = float(np.logaddexp.reduce(lv))
+        self.p = np.exp(lv - self.logvol)
+        self.d = d
+
+    def draw(self, n: int, rng, max_tries: int = 200) -> np.ndarray:
+        """n points uniform in (union of ellipsoids) x [0,1]^d."""
+        out = np.empty((0, self.d))
+        want = n
+        for _ in range(max_tries):
+            m = max(2*want, 16)
+            if len(self.ells) == 1:
+                u = self.ells[0].draw(m, rng)
+            else:
+                which = rng.random(m) < self.p[1]
+                u = np.where(which[:, None], self.ells[1].draw(m, rng), self.ells[0].draw(m, rng))
+                k = self.ells[0].contains(u).astype(int) + self.ells[1].contains(u).astype(int)
+                u = u[rng.random(m)*np.maximum(k, 1) < 1.0]
+            u = u[np.all((u >= 0.0) & (u < 1.0), axis=1)]
+            out = np.concatenate([out, u[:want]])
+            want = n - out.shape[0]
+            if want <= 0:
+                return out
+        raise RuntimeError("nested sampling: the bounding ellipsoid lies almost entirely outside the unit cube")
+
+
+def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int, *, nlive: int = 300,
+                  batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0, maxiter: int = 0,
+                  transform: Optional[Callable[[np.ndarray], np.ndarray]] = None, split: bool = True,
+                  callback: Optional[Callable[[dict], None]] = None, update_interval: int = 0) -> NestedResult:
+    """Nested sampling of a likelihood over the unit cube [0,1)^ndims.
+
+    loglike_batch : callable([n][ndims] float64) -> [n] log-likelihoods; called
+                    with ``batch`` points per step (``nlive`` points at start,
+                    in chunks of ``batch``)
+    transform     : optional unit cube -> physical parameters, applied to the
+                    returned samples (one point per call)
+    tol           : stop when the live points can raise ln Z by less than this
+    eff           : target efficiency; the bound's volume is enlarged by 1/eff
+    maxiter       : stop after this many dead points (0 = no limit)
+    """
+    if ndims < 1 or nlive < 2 or batch < 1:
+        raise ValueError("nested_sample: need ndims >= 1, nlive >= 2, batch >= 1")
+    if not 0.0 < eff <= 1.0:
+        raise ValueError("nested_sample: eff must be in (0, 1]")
+    rng = np.random.default_rng(seed)
+
+    live_u = rng.random((nlive, ndims))
+    live_l = np.empty(nlive)
+    nevals = nbatches = 0
+    for i in range(0, nlive, batch):
+        live_l[i:i + batch] = np.asarray(loglike_batch(live_u[i:i + batch]), dtype=np.float64)
+        nbatches += 1
+    nevals += nlive
+    if np.isnan(live_l).any():
+        raise ValueError("nested_sample: the likelihood returned NaN")
+
+    dead_u, dead_l, dead_lw = [], [], []
+    logz = -math.inf
+    h = 0.0
+    logx = 0.0                                   # ln prior volume left
+    # ln(X_{i-1} - X_i) for X_i = exp(-i/nlive)
+    log_dx_factor = math.log1p(-math.exp(-1.0/nlive))
+    accepted = proposed = 0
+    niter = 0
+    enlarge = 1.0/eff
+
+    def add_weight(ll: float, logw: float):
+        """Accumulate ln Z and the information H (Skilling 2006, eq. 14 ff.)."""
+        nonlocal logz, h
+        new = _logaddexp(logz, ll + logw)
+        if new == -math.inf:
+            return
+        t_new = math.exp(ll + logw - new)*ll if ll > -math.inf else 0.0
+        t_old = math.exp(logz - new)*(h + logz) if logz > -math.inf else 0.0
+        h = t_new + t_old - new
+        logz = new
+
+    done = False
+    while not done:
+        # bound from the current live points; while it is no smaller than the
+        # cube itself, draw from the cube
+        bound = _Bound(live_u, enlarge, rng, split)
+        if bound.logvol >= 0.0:
+            cand = rng.random((batch, ndims))
+        else:
+            cand = bound.draw(batch, rng)
+        cl = np.asarray(loglike_batch(cand), dtype=np.float64)
+        nevals += batch
+        nbatches += 1
+        proposed += batch
+        if np.isnan(cl).any():
+            raise ValueError("nested_sample: the likelihood returned NaN")
+        for u, ll in zip(cand, cl):
+            worst = int(np.argmin(live_l))
+            lmin = live_l[worst]
+            if not ll > lmin:
+                continue
+            # the worst live point dies with weight L_min (X_{i-1} - X_i)
+            logw = logx + log_dx_factor
+            add_weight(lmin, logw)
+            dead_u.append(live_u[worst].copy())
+            dead_l.append(lmin)
+            dead_lw.append(lmin + logw)
+            live_u[worst] = u
+            live_l[worst] = ll
+            logx -= 1.0/nlive
+            niter += 1
+            accepted += 1
+            # termination: what the live points could still add (MultiNest's tol)
+            remain = live_l.max() + logx
+            if logz > -math.inf and _logaddexp(logz, remain) - logz < tol:
+                done = True
+                break
+            if maxiter and niter >= maxiter:
+                done = True
+                break
+        if callback is not None and (update_interval <= 0 or nbatches % update_interval == 0 or done):
+            callback(dict(niter=niter, nevals=nevals, nbatches=nbatches, logz=logz, logx=logx,
+                          lmax=float(live_l.max()), efficiency=accepted/max(proposed, 1)))
+
+    # the live points share what is left of the prior volume
+    logw_live = logx - math.log(nlive)
+    order = np.argsort(live_l)
+    for i in order:
+        add_weight(live_l[i], logw_live)
+        dead_u.append(live_u[i].copy())
+        dead_l.append(live_l[i])
+        dead_lw.append(live_l[i] + logw_live)
+
+    samples = np.array(dead_u)
+    ll = np.array(dead_l)
+    logwt = np.array(dead_lw) - logz
+    phys = np.stack([np.asarray(transform(s), dtype=np.float64) for s in samples]) if transform is not None else None
+    return NestedResult(logz=logz, logz_err=math.sqrt(max(h, 0.0)/nlive), information=h, samples=samples, physical=phys,
+                        loglike=ll, logwt=logwt, niter=niter, nevals=nevals, nbatches=nbatches,
+                        efficiency=accepted/max(proposed, 1))
+
+
+def run(like, *, nlive: int = 300, batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0,
+        maxiter: int = 0, evaluate: Optional[Callable[[np.ndarray], np.ndarray]] = None, **kw) -> NestedResult:
+    """Sample a ``lensed_b200.host.Likelihood``: priors and the parameter map
+    turn each unit-cube point into the float32 parameter vector of the model
+    (src/nested.c:43-74), the whole batch goes through ``loglike_batch`` in one
+    call.  ``evaluate`` replaces the model call, e.g. by
+    ``ShardedLikelihood.for_model(model).loglike_batch`` with one process per
+    GPU (every rank then runs this function with the same seed)."""
+    ev = evaluate if evaluate is not None else like.model.loglike_batch
+
+    def lb(cubes: np.ndarray) -> np.ndarray:
+        P = np.stack([like.device_params(like.physical(c)) for c in cubes])
+        return np.asarray(ev(P), dtype=np.float64)
+
+    return nested_sample(lb, like.ndims, nlive=nlive, batch=batch, tol=tol, eff=eff, seed=seed, maxiter=maxiter,
+                         transform=like.physical, **kw)
+
+
+def write_multinest(root: str, res: NestedResult, labels: Optional[Sequence[str]] = None, seed: int = 0):
+    """MultiNest-layout result files (what the reference leaves behind for its
+    users' tools): ``<root>.txt`` = weight, -2 ln L, parameters;
+    ``<root>post_equal_weights.dat`` = parameters, ln L;
+    ``<root>stats.dat`` = evidence, mean / sigma, maximum-likelihood point."""
+    x = res.physical if res.physical is not None else res.samples
+    w = res.weights
+    with open(root + ".txt", "w") as f:
+        for wi, li, xi in zip(w, res.loglike, x):
+            f.write(" ".join(f"{v: .18E}" for v in (wi, -2.0*li, *xi)) + "\n")
+    idx = res.equal_weights(seed)
+    with open(root + "post_equal_weights.dat", "w") as f:
+        for i in idx:
+            f.write(" ".join(f"{v: .18E}" for v in (*x[i], res.loglike[i])) + "\n")
+    mean, sigma, ml = res.mean(), res.std(), res.max_like()
+    with open(root + "stats.dat", "w") as f:
+        f.write(f"Nested Sampling Global Log-Evidence           :  {res.logz: .18E}  +/-  {res.logz_err: .18E}\n\n")
+        f.write("Dim No.       Mean        Sigma\n")
+        for i, (m, s) in enumerate(zip(mean, sigma), 1):
+            f.write(f"{i:5d}  {m: .18E}  {s: .18E}\n")
+        f.write("\nMaximum Likelihood Parameters\nDim No.        Parameter\n")
+        for i, v in enumerate(ml, 1):
+            f.write(f"{i:5d}  {v: .18E}\n")
+        if labels:
+            f.write("\n" + "\n".join(f"# {i}: {lab}" for i, lab in enumerate(labels, 1)) + "\n")

@@ -87,3 +87,44 @@ def test_two_ranks_gloo(mode):
         assert [c for _, _, c in res] == [[2], [3]]          # 5 points -> slices of 2 and 3
     else:
         assert [c for _, _, c in res] == [[0, 24], [24, 48]]
+
+
+def _sampler_worker(rank, world, port, q):
+    import math
+    import torch.distributed as dist
+    from lensed_b200.distributed import ShardedLikelihood
+    from lensed_b200 import sampler as S
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        seen = []
+
+        def evaluate(p):
+            # this rank's slice of the batch only (float32 parameters, as the model gets them)
+            seen.append(p.shape[0])
+            p = p.astype(np.float64)
+            return -0.5*(((p - 0.5)/0.05)**2).sum(axis=1) - p.shape[1]*math.log(0.05*math.sqrt(2*math.pi))
+        sh = ShardedLikelihood(evaluate, mode="points")
+        r = S.nested_sample(sh.loglike_batch, 2, nlive=100, batch=16, seed=7)
+        q.put((rank, r.logz, r.logz_err, r.niter, sum(seen), r.nevals))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sampler_two_ranks_same_chain_half_the_work_each():
+    """One sampler per rank, same seed: the all-reduced batch is identical on
+    both ranks, so both follow the same chain while each evaluates half of
+    every batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, z0, e0, n0, w0, t0), (_, z1, e1, n1, w1, t1) = res
+    assert z0 == z1 and n0 == n1 and t0 == t1
+    assert w0 + w1 == t0 and abs(w0 - w1) <= 8
+    assert abs(z0) < 4*e0 + 0.05

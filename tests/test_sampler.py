@@ -1,0 +1,139 @@
+"""Batch-native nested sampler (lensed_b200/sampler.py) against analytic
+evidences; the likelihood is a host function here, so no GPU is needed.  The
+GPU test at the end runs it on a small lens model through lcu_loglike_batch."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from lensed_b200 import sampler as S
+
+
+def _gauss(mu, sig):
+    mu, sig = np.asarray(mu, float), np.asarray(sig, float)
+
+    def f(u):
+        u = np.atleast_2d(u)
+        return -0.5*(((u - mu)/sig)**2).sum(axis=1) - np.log(sig*math.sqrt(2*math.pi)).sum()
+    return f
+
+
+def test_gaussian_evidence_and_moments():
+    """Normalised Gaussian well inside the unit cube: Z = 1."""
+    calls = []
+    f = _gauss([0.4, 0.6, 0.5], [0.02, 0.05, 0.03])
+
+    def lb(u):
+        calls.append(len(u))
+        return f(u)
+    r = S.nested_sample(lb, 3, nlive=400, batch=64, tol=0.01, seed=3)
+    assert abs(r.logz) < 4*r.logz_err + 0.05, (r.logz, r.logz_err)
+    assert np.allclose(r.mean(), [0.4, 0.6, 0.5], atol=0.005)
+    assert np.allclose(r.std(), [0.02, 0.05, 0.03], rtol=0.15)
+    # information of a Gaussian w.r.t. a unit prior: H = -ln((2 pi e)^(d/2) |Sigma|^(1/2))
+    h = -(1.5*math.log(2*math.pi*math.e) + math.log(0.02*0.05*0.03))
+    assert abs(r.information - h) < 0.3
+    # every call after the initial live points is one full batch
+    assert set(calls[7:]) == {64} and sum(calls) == r.nevals and len(calls) == r.nbatches
+    assert abs(np.exp(r.logwt).sum() - 1) < 1e-9
+    assert r.efficiency > 0.2
+
+
+def test_same_seed_same_run_and_batch_size_independent_answer():
+    f = _gauss([0.5, 0.5], [0.05, 0.1])
+    a = S.nested_sample(f, 2, nlive=200, batch=32, seed=11)
+    b = S.nested_sample(f, 2, nlive=200, batch=32, seed=11)
+    assert a.logz == b.logz and np.array_equal(a.samples, b.samples)
+    c = S.nested_sample(f, 2, nlive=200, batch=1, seed=12)       # one point per call, MultiNest style
+    d = S.nested_sample(f, 2, nlive=200, batch=256, seed=13)
+    for r in (a, c, d):
+        assert abs(r.logz) < 4*r.logz_err + 0.05
+    assert d.nbatches < c.nbatches/50
+
+
+def test_two_modes_are_both_found():
+    f1, f2 = _gauss([0.25, 0.3], [0.02, 0.02]), _gauss([0.75, 0.7], [0.02, 0.02])
+
+    def lb(u):
+        return np.logaddexp(f1(u), f2(u)) - math.log(2)
+    r = S.nested_sample(lb, 2, nlive=400, batch=64, seed=5)
+    assert abs(r.logz) < 4*r.logz_err + 0.05
+    w = r.weights
+    left = w[r.samples[:, 0] < 0.5].sum()
+    assert 0.35 < left < 0.65
+
+
+def test_maxiter_transform_and_files(tmp_path):
+    f = _gauss([0.5], [0.1])
+    r = S.nested_sample(f, 1, nlive=50, batch=8, seed=1, maxiter=100, transform=lambda u: np.array([10*u[0], 7.0]))
+    assert r.niter == 100 and r.samples.shape == (150, 1) and r.physical.shape == (150, 2)
+    assert np.all(r.physical[:, 1] == 7.0) and np.allclose(r.physical[:, 0], 10*r.samples[:, 0])
+    S.write_multinest(str(tmp_path / "run-"), r, labels=["x", "const"])
+    txt = np.loadtxt(tmp_path / "run-.txt")
+    assert txt.shape == (150, 4) and abs(txt[:, 0].sum() - 1) < 1e-9
+    assert np.allclose(txt[:, 1], -2*r.loglike)
+    assert "Global Log-Evidence" in open(tmp_path / "run-stats.dat").read()
+    pew = np.loadtxt(tmp_path / "run-post_equal_weights.dat", ndmin=2)
+    assert pew.shape[1] == 3 and len(pew) > 5
+    with pytest.raises(ValueError):
+        S.nested_sample(f, 1, nlive=1)
+    with pytest.raises(ValueError):
+        S.nested_sample(lambda u: np.full(len(u), np.nan), 1, nlive=10)
+
+
+def test_run_maps_cube_to_device_parameters():
+    """sampler.run() feeds the model's batched entry point with float32
+    parameter vectors in object order (free dimensions first in the cube,
+    derived parameters last: src/lensed.c:236-271, src/nested.c:43-74)."""
+    from lensed_b200 import host as Hh
+
+    class FakeModel:
+        def __init__(self):
+            self.seen = []
+
+        def loglike_batch(self, P):
+            assert P.dtype == np.float32 and P.shape[1] == 3
+            self.seen.append(P.copy())
+            return -0.5*((P[:, 0] - 3.0)/0.2)**2 - 0.5*((P[:, 2] - 1.0)/0.1)**2
+
+    pars = [Hh.Parameter("a.x", "x", 0, 0, 0, Hh.Uniform(0, 10)), Hh.Parameter("a.k", "k", 0, 0, 0, Hh.Delta(5.0)),
+            Hh.Parameter("a.z", "z", 0, 0, 0, Hh.Uniform(0, 2))]
+    cfg = Hh.Config({}, [Hh.ObjectEntry("a", "fake", "S", pars)])
+    fm = FakeModel()
+    like = Hh.Likelihood(cfg, fm)
+    assert like.ndims == 2 and like.npars == 3
+    r = S.run(like, nlive=100, batch=16, seed=2)
+    assert all(np.all(P[:, 1] == 5.0) for P in fm.seen)
+    m = r.mean()            # sampler order: x, z, then the derived k
+    assert abs(m[0] - 3.0) < 0.05 and abs(m[1] - 1.0) < 0.03 and abs(m[2] - 5.0) < 1e-9
+    # Z = integral of L over the prior = (0.2 sqrt(2 pi)/10) (0.1 sqrt(2 pi)/2)
+    z = math.log(0.2*math.sqrt(2*math.pi)/10) + math.log(0.1*math.sqrt(2*math.pi)/2)
+    assert abs(r.logz - z) < 4*r.logz_err + 0.05
+
+
+@pytest.mark.gpu
+def test_sampler_on_a_lens_model(gpu_ctx):
+    """Three free parameters of a small SIE + Sersic scene: the posterior
+    brackets the truth, every step is one batched launch."""
+    import helpers as H
+    import lensed_b200 as L
+    cfg = H.synthetic_config("c4", 64, psf_shape=(5, 5))
+    m = cfg.product(gpu_ctx)
+    truth = cfg.params.astype(np.float64)
+    free = [2, 3, 10]                         # lens radius, lens axis ratio, source magnitude
+    span = [1.0, 0.1, 0.3]
+    n0 = L.launch_count()
+
+    def lb(u):
+        P = np.tile(truth, (len(u), 1))
+        for k, (i, s) in enumerate(zip(free, span)):
+            P[:, i] = truth[i] + (u[:, k] - 0.5)*2*s
+        return m.loglike_batch(P.astype(np.float32))
+    r = S.nested_sample(lb, 3, nlive=100, batch=50, tol=0.5, seed=4)
+    launches = L.launch_count() - n0
+    assert launches <= 5*r.nbatches                       # set_params, copy-free render, convolve, reduce per batch
+    mean, std = r.mean(), r.std()
+    assert np.all(np.abs(mean - 0.5) < 5*std + 0.02), (mean, std)
+    assert np.all(std < 0.2)
+    assert r.nevals == 100 + 50*(r.nbatches - 2)
