@@ -70,6 +70,9 @@ bool compile_cubin(const std::string& source, const std::vector<Header>& headers
 bool cubin_symbol(const std::vector<char>& cubin, const std::string& symbol,
                   const unsigned char** bytes, size_t* size);
 
+// registers per thread and stack bytes of a kernel of a cubin (.nv.info records)
+bool cubin_kernel_usage(const std::vector<char>& cubin, const std::string& kernel, unsigned* regs, unsigned* stack);
+
 // quadrature -------------------------------------------------------------------
 int quad_rule_count();
 const char* quad_rule_name(int i);

@@ -510,6 +510,79 @@ bool cubin_symbol(const std::vector<char>& cubin, const std::string& symbol,
     return false;
 }
 
+// Registers per thread and stack (spill) bytes of a kernel, from the
+// EIATTR_REGCOUNT (0x2f) / EIATTR_MIN_STACK_SIZE (0x12) records of the cubin's
+// .nv.info section; both carry (symbol index, value).
+bool cubin_kernel_usage(const std::vector<char>& cubin, const std::string& kernel, unsigned* regs, unsigned* stack)
+{
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(cubin.data());
+    const size_t len = cubin.size();
+    if(len < sizeof(Elf64Ehdr) || memcmp(base, "\177ELF", 4) != 0 || base[4] != 2)
+        return false;
+    Elf64Ehdr eh;
+    memcpy(&eh, base, sizeof(eh));
+    if(eh.shoff == 0 || eh.shentsize != sizeof(Elf64Shdr) || eh.shoff + (uint64_t)eh.shnum*sizeof(Elf64Shdr) > len
+       || eh.shstrndx >= eh.shnum)
+        return false;
+    std::vector<Elf64Shdr> sh(eh.shnum);
+    memcpy(sh.data(), base + eh.shoff, eh.shnum*sizeof(Elf64Shdr));
+    // symbol index of the kernel
+    long symidx = -1;
+    for(const Elf64Shdr& st : sh)
+    {
+        if(st.type != 2 /* SHT_SYMTAB */ || st.link >= sh.size() || st.entsize != sizeof(Elf64Sym))
+            continue;
+        const Elf64Shdr& str = sh[st.link];
+        if(st.offset + st.size > len || str.offset + str.size > len)
+            return false;
+        for(size_t i = 0; i < st.size/sizeof(Elf64Sym); ++i)
+        {
+            Elf64Sym sym;
+            memcpy(&sym, base + st.offset + i*sizeof(Elf64Sym), sizeof(sym));
+            if(sym.name < str.size && (sym.info & 0xf) == 2 /* STT_FUNC */
+               && kernel == reinterpret_cast<const char*>(base + str.offset + sym.name))
+                symidx = (long)i;
+        }
+    }
+    if(symidx < 0)
+        return false;
+    const Elf64Shdr& names = sh[eh.shstrndx];
+    bool have_regs = false, have_stack = false;
+    for(const Elf64Shdr& sec : sh)
+    {
+        if(sec.name >= names.size || sec.offset + sec.size > len)
+            continue;
+        if(strcmp(reinterpret_cast<const char*>(base + names.offset + sec.name), ".nv.info") != 0)
+            continue;
+        const unsigned char* d = base + sec.offset;
+        for(size_t i = 0; i + 4 <= sec.size; )
+        {
+            const unsigned fmt = d[i], attr = d[i + 1];
+            if(fmt != 4)        // formats 1-3 carry their value in the 4-byte record itself
+            {
+                i += 4;
+                continue;
+            }
+            uint16_t sz;
+            memcpy(&sz, d + i + 2, 2);
+            if(i + 4 + sz > sec.size)
+                break;
+            if(sz == 8 && (attr == 0x2f || attr == 0x12))
+            {
+                uint32_t v[2];
+                memcpy(v, d + i + 4, 8);
+                if((long)v[0] == symidx)
+                {
+                    if(attr == 0x2f) { *regs = v[1]; have_regs = true; }
+                    else { *stack = v[1]; have_stack = true; }
+                }
+            }
+            i += 4 + sz;
+        }
+    }
+    return have_regs && have_stack;
+}
+
 } // namespace lcu
 
 // ---------------------------------------------------------------------------

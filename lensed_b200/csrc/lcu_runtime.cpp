@@ -824,6 +824,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
 
     // program text: main_program(), src/kernel.c:838-879 -- ABI headers,
     // each distinct object once, compute, set_params, kernels
+    auto assemble = [&](int pair_minblocks)
     {
         std::ostringstream s;
         // kernel_options(), src/kernel.c:881-944
@@ -840,8 +841,10 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "#define LCU_NPARS " << std::max<size_t>(m->npars, 1) << "\n"
           << "#define LCU_MAXB " << m->maxb << "\n"
           << "#define LCU_OBJ_CONST " << (m->obj_const ? 1 : 0) << "\n"
-          << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n"
-          << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
+          << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n";
+        if(pair_minblocks)
+            s << "#define LCU_PAIR_MINBLOCKS " << pair_minblocks << "\n";
+        s << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
         std::vector<const ObjectInfo*> uniq;
         for(const ModelObject& o : m->objs)
             if(std::find(uniq.begin(), uniq.end(), o.info) == uniq.end())
@@ -862,14 +865,38 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "//----------------------------------------------------------------------------\n"
           << "#line 1 \"kernel/lensed.cu\"\n"
           << ctx->kernels;
-        m->source = s.str();
-    }
+        return s.str();
+    };
 
+    m->source = assemble(0);
     if(!ctx->compile(m->source, m->flags, &m->cubin, &m->log))
     {
         set_error("failed to build program\n%s", m->log.c_str());
         delete m;
         return LCU_E_COMPILE;
+    }
+    // The two-rays kernel is built for 3 resident blocks per SM (80 registers).
+    // A model whose ray function needs many more (epl_plus_shear + 3 sources:
+    // ~125) would spill inside the ray loop: build it for 2 blocks instead if
+    // that removes the spills.
+    if(m->pair)
+    {
+        const char* extra = getenv("LCU_NVRTC_FLAGS");
+        unsigned regs = 0, stack = 0, regs2 = 0, stack2 = 0;
+        if(!(extra && strstr(extra, "LCU_PAIR_MINBLOCKS")) && cubin_kernel_usage(m->cubin, "lcu_render_pair", &regs, &stack)
+           && stack > 64)
+        {
+            const std::string src2 = assemble(2);
+            std::vector<char> cubin2;
+            std::string log2;
+            if(ctx->compile(src2, m->flags, &cubin2, &log2) && cubin_kernel_usage(cubin2, "lcu_render_pair", &regs2, &stack2)
+               && stack2 < stack)
+            {
+                m->source = src2;
+                m->cubin.swap(cubin2);
+                m->log = log2;
+            }
+        }
     }
 
     if(ctx->device < 0)
