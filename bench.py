@@ -285,11 +285,14 @@ def run_gpu(args):
         conv_ms = prof["convolve_ms"]/nchunk
         render_flops = work["render_flops"]*B
         achieved = render_flops/(render_ms*1e-3)/1e12 if render_ms > 0 else None
-        traffic = None
+        traffic = pipe_busy = None
         tpath = os.path.join(ROOT, "profiles", "render_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"{args.workload}_B{B}")
+                tj = json.load(open(tpath))
+                traffic = tj.get(f"{args.workload}_B{B}")
+                if flags != 0 and model.rays_per_thread == 2:
+                    pipe_busy = tj.get(f"{args.workload}_fp32_pipe_busy")
             except Exception:
                 traffic = None
         line = {
@@ -317,6 +320,9 @@ def run_gpu(args):
                 "algorithmic": f"{w['flops_per_ray']} flop + {w['transc_per_ray']} transcendental calls per ray x "
                                f"{work['rays']} rays x {B} points per launch",
                 "launch_ms": render_ms,
+                # share of cycles the FP32 pipe is busy, from the committed ncu capture of this kernel
+                # (profiles/): the instruction-level roofline; `frac` counts source-level flops only
+                "fp32_pipe_busy_ncu": pipe_busy,
                 "transc_calls_per_s": work["transc"]*B/(render_ms*1e-3) if render_ms > 0 else None,
                 "grays_per_s_kernel": work["rays"]*B/(render_ms*1e-3)/1e9 if render_ms > 0 else None,
             },
