@@ -191,6 +191,22 @@ size_t lcu_model_cubin(const lcu_model* model, const void** image);
 int lcu_model_set_rows(lcu_model* model, size_t row0, size_t row1);
 
 /*
+ * Data preparation on the device (once per run, off the likelihood path).
+ * lcu_model_set_data replaces the observed image and / or the weight map of an
+ * existing model (either pointer may be NULL = keep): same kernels, no
+ * recompilation, e.g. for a series of mock observations.  lcu_model_make_weight
+ * builds the weight map from the image held by the model as make_weight() does
+ * (src/data.c:314-330): weight = gain / (image + offset), evaluated in double and
+ * narrowed to float, with gain a per-pixel map or, if gain_map is NULL, one value
+ * (make_real(), src/data.c:286-311); pixels with a non-zero mask entry get
+ * weight 0 (src/lensed.c:470-482; mask may be NULL).  lcu_model_get_weight
+ * reads the current map back (the dumper's WHT layer, src/nested.c:236).
+ */
+int lcu_model_set_data(lcu_model* model, const float* image, const float* weight);
+int lcu_model_make_weight(lcu_model* model, const float* gain_map, float gain, double offset, const int* mask);
+int lcu_model_get_weight(lcu_model* model, float* weight);
+
+/*
  * One likelihood evaluation: replaces the device part of loglike(),
  * src/nested.c:63-115.  params[npars] are the physical parameters in object
  * order, i.e. what the reference writes into its mapped buffer at

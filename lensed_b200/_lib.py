@@ -72,6 +72,9 @@ SYMBOLS = {
     "lcu_model_build_log": (C.c_char_p, [C.c_void_p]),
     "lcu_model_cubin": (C.c_size_t, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "lcu_model_set_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "lcu_model_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lcu_model_make_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_void_p]),
+    "lcu_model_get_weight": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lcu_loglike": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "lcu_loglike_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "lcu_loglike_batch_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),

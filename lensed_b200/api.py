@@ -209,6 +209,40 @@ class Model:
     def set_rows(self, row0: int, row1: int):
         check(lib.lcu_model_set_rows(self._h, int(row0), int(row1)))
 
+    def set_data(self, image=None, weight=None):
+        """Replace the observed image and / or the weight map (same size)."""
+        for a in (image, weight):
+            if a is not None and np.asarray(a).shape != (self.height, self.width):
+                raise ValueError("set_data: array shape differs from the model's image")
+        im = _f32(image) if image is not None else None
+        wt = _f32(weight) if weight is not None else None
+        check(lib.lcu_model_set_data(self._h, _ptr(im), _ptr(wt)))
+
+    def make_weight(self, gain, offset: float = 0.0, mask=None) -> np.ndarray:
+        """weight = gain / (image + offset) on the device (src/data.c:314-330);
+        gain is a number or a per-pixel map, masked pixels (non-zero) get
+        weight 0 (src/lensed.c:470-482).  Returns the new map."""
+        gm = None
+        g0 = 0.0
+        if np.ndim(gain) == 0:
+            g0 = float(gain)
+        else:
+            gm = _f32(gain)
+            if gm.shape != (self.height, self.width):
+                raise ValueError("make_weight: gain map shape differs from the model's image")
+        mk = None
+        if mask is not None:
+            mk = np.ascontiguousarray(mask, dtype=np.int32)
+            if mk.shape != (self.height, self.width):
+                raise ValueError("make_weight: mask shape differs from the model's image")
+        check(lib.lcu_model_make_weight(self._h, _ptr(gm), C.c_float(g0), C.c_double(offset), _ptr(mk)))
+        return self.weight_map()
+
+    def weight_map(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), np.float32)
+        check(lib.lcu_model_get_weight(self._h, _ptr(out)))
+        return out
+
     def _params(self, params, batch: bool):
         p = _f32(params)
         if batch:

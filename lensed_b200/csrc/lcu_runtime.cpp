@@ -159,6 +159,7 @@ struct lcu_model
     CUmodule mod = nullptr;
     CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_reduce = nullptr;
     CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
+    CUfunction f_make_weight = nullptr;
     bool pair = false;
     CUdeviceptr c_objs = 0;
     cudaStream_t stream = nullptr;
@@ -927,6 +928,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair_err, m->mod, "lcu_render_pair_err")));
     }
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_make_weight, m->mod, "lcu_make_weight")));
     if(m->has_psf)
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv, m->mod, "lcu_convolve")));
 
@@ -1019,6 +1021,77 @@ static int need_device(const lcu_model* m, const char* fn)
         set_error("%s: compile-only context has no device (there is no CPU fallback)", fn);
         return LCU_E_NODEVICE;
     }
+    return LCU_OK;
+}
+
+int lcu_model_set_data(lcu_model* m, const float* image, const float* weight)
+{
+    int rc = need_device(m, "lcu_model_set_data");
+    if(rc) return rc;
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    if(image)
+        RT_CHECK(cudaMemcpy(m->d_image, image, m->size*sizeof(float), cudaMemcpyHostToDevice));
+    if(weight)
+        RT_CHECK(cudaMemcpy(m->d_weight, weight, m->size*sizeof(float), cudaMemcpyHostToDevice));
+    return LCU_OK;
+}
+
+int lcu_model_make_weight(lcu_model* m, const float* gain_map, float gain, double offset, const int* mask)
+{
+    int rc = need_device(m, "lcu_model_make_weight");
+    if(rc) return rc;
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    float* d_gain = nullptr;
+    int* d_mask = nullptr;
+    auto cleanup = [&]() { if(d_gain) cudaFree(d_gain); if(d_mask) cudaFree(d_mask); };
+    if(gain_map)
+    {
+        RT_CHECK(cudaMalloc(&d_gain, m->size*sizeof(float)));
+        if(cudaMemcpyAsync(d_gain, gain_map, m->size*sizeof(float), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+        {
+            cleanup();
+            set_error("lcu_model_make_weight: copy of the gain map failed");
+            return LCU_E_CUDA;
+        }
+    }
+    if(mask)
+    {
+        if(cudaMalloc(&d_mask, m->size*sizeof(int)) != cudaSuccess
+           || cudaMemcpyAsync(d_mask, mask, m->size*sizeof(int), cudaMemcpyHostToDevice, m->stream) != cudaSuccess)
+        {
+            cleanup();
+            set_error("lcu_model_make_weight: copy of the mask failed");
+            return LCU_E_CUDA;
+        }
+    }
+    long long n = (long long)m->size;
+    const unsigned blocks = (unsigned)std::min<size_t>(div_up(m->size, 256), (size_t)std::max(m->ctx->sm_count, 1)*8);
+    void* args[] = { &n, &m->d_image, &d_gain, &gain, &offset, &d_mask, &m->d_weight };
+    rc = launch(m, m->f_make_weight, dim3(blocks), dim3(256), args, m->stream);
+    const cudaError_t e = cudaStreamSynchronize(m->stream);
+    cleanup();
+    if(rc) return rc;
+    if(e != cudaSuccess)
+    {
+        set_error("lcu_model_make_weight: %s", cudaGetErrorString(e));
+        return LCU_E_CUDA;
+    }
+    return LCU_OK;
+}
+
+int lcu_model_get_weight(lcu_model* m, float* weight)
+{
+    int rc = need_device(m, "lcu_model_get_weight");
+    if(rc) return rc;
+    if(!weight)
+    {
+        set_error("lcu_model_get_weight: null output");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    RT_CHECK(cudaMemcpy(weight, m->d_weight, m->size*sizeof(float), cudaMemcpyDeviceToHost));
     return LCU_OK;
 }
 

@@ -506,6 +506,24 @@ lcu_convolve(const __grid_constant__ lcu_convolve_args a)
 #endif // PSF
 
 // ---------------------------------------------------------------------------
+// data preparation: weight map from gain and offset (src/data.c:314-330), masked
+// pixels weight 0 (src/lensed.c:470-482).  Double division, narrowed once.
+// ---------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_make_weight(long long n, const float* __restrict__ image, const float* __restrict__ gain_map, float gain,
+                double offset, const int* __restrict__ mask, float* __restrict__ weight)
+{
+    for(long long i = (long long)blockIdx.x*LCU_BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x*LCU_BLOCK)
+    {
+        const double g = gain_map ? gain_map[i] : gain;
+        float w = (float)(g/((double)image[i] + offset));
+        if(mask && mask[i])
+            w = 0;
+        weight[i] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // final reduction: one block per point, fixed summation shape
 // out[b] = scale * sum_g partial[b][g]   (scale = -0.5 gives the log-likelihood
 // of src/nested.c:115; scale = 1 the chi^2 of one row strip)

@@ -449,3 +449,37 @@ def test_two_rays_per_thread_guard_and_zoo(gpu_ctx, monkeypatch):
     a, b = m2.render(params), m1.render(params)
     for key in ("raw", "error", "model", "chi"):
         assert np.array_equal(a[key].view(np.uint32), b[key].view(np.uint32)), key
+
+
+def test_device_data_preparation(gpu_ctx):
+    """Weight map from gain / offset / mask built on the device
+    (src/data.c:314-330, src/lensed.c:470-482) is the host computation bit for
+    bit; swapping image and weights of a live model gives the log-likelihoods
+    of a model created with them."""
+    cfg = H.synthetic_config("c4", 64, psf_shape=(5, 5))
+    rng = np.random.default_rng(3)
+    gain_map = rng.uniform(500, 3000, cfg.image.shape).astype(np.float32)
+    mask = (rng.random(cfg.image.shape) < 0.1).astype(np.int32)
+    offset = 2.9633
+    m = cfg.product(gpu_ctx)
+    for gain in (np.float32(1800.0), gain_map):
+        for mk in (None, mask):
+            ref = (np.asarray(gain, np.float32).astype(np.float64)/(cfg.image.astype(np.float64) + offset)).astype(np.float32)
+            if mk is not None:
+                ref = np.where(mk != 0, np.float32(0), ref)
+            got = m.make_weight(gain, offset, mk)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    P = H.workloads.param_batch(cfg.extra["workload"], 4)
+    fresh = H.Config("fresh", cfg.objects, cfg.params, cfg.image, ref, rule=cfg.rule, psf=cfg.psf).product(gpu_ctx)
+    assert np.array_equal(m.loglike_batch(P), fresh.loglike_batch(P))
+    assert m.loglike(P[0]) == fresh.loglike(P[0])
+    # another observation into the same model: no recompilation, same answers as a new model
+    img2 = (cfg.image + rng.normal(0, 0.01, cfg.image.shape)).astype(np.float32)
+    w2 = H.workloads.make_weight(img2)
+    m.set_data(image=img2, weight=w2)
+    fresh2 = H.Config("fresh2", cfg.objects, cfg.params, img2, w2, rule=cfg.rule, psf=cfg.psf).product(gpu_ctx)
+    assert np.array_equal(m.loglike_batch(P), fresh2.loglike_batch(P))
+    assert m.loglike(P[1]) == fresh2.loglike(P[1])        # the single-point graph sees the new data too
+    assert np.array_equal(m.weight_map(), w2)
+    with pytest.raises(ValueError):
+        m.set_data(image=np.zeros((3, 3), np.float32))
