@@ -216,15 +216,29 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         raise ValueError("nested_sample: eff must be in (0, 1]")
     rng = np.random.default_rng(seed)
 
+    nan_points = 0
+
+    def evaluate(u: np.ndarray) -> np.ndarray:
+        """One batched launch; a NaN likelihood (a parameter point at which the
+        model itself is undefined, e.g. axis ratio 0) counts as zero
+        likelihood, as MultiNest's logzero does (src/lensed.c:1244)."""
+        nonlocal nan_points
+        ll = np.array(loglike_batch(u), dtype=np.float64)
+        bad = np.isnan(ll)
+        if bad.any():
+            nan_points += int(bad.sum())
+            ll[bad] = -math.inf
+        return ll
+
     live_u = rng.random((nlive, ndims))
     live_l = np.empty(nlive)
     nevals = nbatches = 0
     for i in range(0, nlive, batch):
-        live_l[i:i + batch] = np.asarray(loglike_batch(live_u[i:i + batch]), dtype=np.float64)
+        live_l[i:i + batch] = evaluate(live_u[i:i + batch])
         nbatches += 1
     nevals += nlive
-    if np.isnan(live_l).any():
-        raise ValueError("nested_sample: the likelihood returned NaN")
+    if not np.isfinite(live_l).any():
+        raise ValueError("nested_sample: the likelihood is NaN or zero at every initial live point")
 
     dead_u, dead_l, dead_lw = [], [], []
     logz = -math.inf
@@ -256,12 +270,10 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
             cand = rng.random((batch, ndims))
         else:
             cand = bound.draw(batch, rng)
-        cl = np.asarray(loglike_batch(cand), dtype=np.float64)
+        cl = evaluate(cand)
         nevals += batch
         nbatches += 1
         proposed += batch
-        if np.isnan(cl).any():
-            raise ValueError("nested_sample: the likelihood returned NaN")
         for u, ll in zip(cand, cl):
             worst = int(np.argmin(live_l))
             lmin = live_l[worst]
@@ -305,7 +317,7 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     phys = np.stack([np.asarray(transform(s), dtype=np.float64) for s in samples]) if transform is not None else None
     return NestedResult(logz=logz, logz_err=math.sqrt(max(h, 0.0)/nlive), information=h, samples=samples, physical=phys,
                         loglike=ll, logwt=logwt, niter=niter, nevals=nevals, nbatches=nbatches,
-                        efficiency=accepted/max(proposed, 1))
+                        efficiency=accepted/max(proposed, 1), stats={"nan_points": nan_points})
 
 
 def run(like, *, nlive: int = 300, batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0,

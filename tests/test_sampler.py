@@ -82,6 +82,21 @@ def test_maxiter_transform_and_files(tmp_path):
         S.nested_sample(lambda u: np.full(len(u), np.nan), 1, nlive=10)
 
 
+def test_nan_likelihood_counts_as_zero():
+    """Points where the model is undefined (NaN) are treated like MultiNest's
+    logzero: never accepted, zero weight; the evidence is that of the rest."""
+    g = _gauss([0.5, 0.5], [0.05, 0.05])
+
+    def lb(u):
+        ll = g(u)
+        ll[u[:, 0] < 0.1] = np.nan
+        return ll
+    r = S.nested_sample(lb, 2, nlive=200, batch=32, seed=9)
+    assert r.stats["nan_points"] > 0
+    assert abs(r.logz) < 4*r.logz_err + 0.05
+    assert np.all(r.weights[r.samples[:, 0] < 0.1] == 0)
+
+
 def test_run_maps_cube_to_device_parameters():
     """sampler.run() feeds the model's batched entry point with float32
     parameter vectors in object order (free dimensions first in the cube,
