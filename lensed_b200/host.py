@@ -38,6 +38,10 @@ class Prior:
     def apply(self, u: float) -> float:
         raise NotImplementedError
 
+    def apply_many(self, u):
+        """apply() for an array of unit-interval values (batched samplers)."""
+        return np.array([self.apply(float(v)) for v in np.asarray(u).ravel()], np.float64).reshape(np.shape(u))
+
     def lower(self) -> float:
         raise NotImplementedError
 
@@ -56,6 +60,9 @@ class Delta(Prior):
     def apply(self, u):
         return self.value
 
+    def apply_many(self, u):
+        return np.full(np.shape(u), self.value, np.float64)
+
     def lower(self):
         return self.value
 
@@ -69,6 +76,9 @@ class Uniform(Prior):
 
     def apply(self, u):
         return self.a + u*(self.b - self.a)          # src/prior/unif.c:68-73
+
+    def apply_many(self, u):
+        return self.a + np.asarray(u, np.float64)*(self.b - self.a)
 
     def lower(self):
         return self.a
@@ -91,6 +101,14 @@ class Normal(Prior):
 
     def apply(self, u):
         return self.m + self.s*self._gauss(u)         # src/prior/norm.c:77-82
+
+    def apply_many(self, u):
+        # the same rational approximation, element-wise
+        u = np.asarray(u, np.float64)
+        low = u < 0.5
+        t = np.sqrt(-2.0*np.log(np.where(low, u, 1 - u)))
+        t = t - ((0.010328*t + 0.802853)*t + 2.515517)/(((0.001308*t + 0.189269)*t + 1.432788)*t + 1.0)
+        return self.m + self.s*np.where(low, -t, t)
 
     def lower(self):
         return self.m - 7*self.s
@@ -279,13 +297,35 @@ class Likelihood:
             params[self.pmap[i]] = phys[i]
         return params
 
+    def physical_batch(self, cubes) -> np.ndarray:
+        """physical() for [n][ndims] unit-cube points at once -> [n][npars],
+        sampler order.  Points outside a parameter's hard bounds raise, as
+        physical() does."""
+        cubes = np.atleast_2d(np.asarray(cubes, np.float64))
+        out = np.empty((cubes.shape[0], self.npars), np.float64)
+        for i in range(self.npars):
+            par = self.pars[self.pmap[i]]
+            u = cubes[:, i] if i < self.ndims else np.full(cubes.shape[0], 0.5)
+            phys = par.prior.apply_many(u)
+            if par.bounded and ((phys < par.lower) | (phys > par.upper)).any():
+                bad = phys[(phys < par.lower) | (phys > par.upper)][0]
+                raise ValueError(f"{par.id}: value {bad:g} outside parameter bounds [{par.lower:g}, {par.upper:g}]")
+            out[:, i] = phys
+        return out
+
+    def device_params_batch(self, phys) -> np.ndarray:
+        """[n][npars] sampler order -> object order, float32."""
+        phys = np.atleast_2d(phys)
+        params = np.empty(phys.shape, np.float32)
+        params[:, self.pmap] = phys
+        return params
+
     def __call__(self, cube) -> float:
         return self.model.loglike(self.device_params(self.physical(cube)))
 
     def batch(self, cubes) -> np.ndarray:
         """Many points per launch: the batched entry point."""
-        P = np.stack([self.device_params(self.physical(c)) for c in cubes])
-        return self.model.loglike_batch(P)
+        return self.model.loglike_batch(self.device_params_batch(self.physical_batch(cubes)))
 
 
 def build(path: str, ctx: Context, **model_kw):

@@ -8,12 +8,12 @@ likelihood, draws the next.  A GPU wants the opposite: ``lcu_loglike_batch``
 evaluates B points per launch (include/lensed_cuda.h).  This module is the
 driver that produces such batches: the nested
 sampling algorithm of Skilling (2004) with MultiNest's ellipsoidal rejection
-scheme (Feroz & Hobson 2008, the single-ellipsoid case, optionally split in
-two by k-means when that shrinks the volume), restated so that the B candidate
+scheme (Feroz & Hobson 2008: the live points are partitioned recursively by
+2-means into ellipsoids while that shrinks the bounded volume), restated so that the B candidate
 points of one step are drawn *before* any of them is evaluated:
 
-    bound   = enlarged ellipsoid around the live points (intersected with the
-              unit cube)
+    bound   = union of enlarged ellipsoids around clusters of the live points
+              (intersected with the unit cube)
     cand    = B points uniform in bound                    -> one batched launch
     for c in cand, in the order drawn:
         if L(c) > L_min(live): the worst live point dies (weight L_min dX),
@@ -102,7 +102,7 @@ class _Ellipsoid:
     its volume is `enlarge` times that of the smallest similar ellipsoid
     containing them all."""
 
-    def __init__(self, pts: np.ndarray, enlarge: float):
+    def __init__(self, pts: np.ndarray, enlarge: float, min_logvol: float = -math.inf):
         n, d = pts.shape
         self.d = d
         self.c = pts.mean(axis=0)
@@ -117,6 +117,12 @@ class _Ellipsoid:
         k = max(k, 1e-300)*enlarge**(2.0/d)
         self.L = np.linalg.cholesky(cov*k)                            # A = L L^T
         self.logvol = float(np.log(np.diag(self.L)).sum()) + _log_unit_ball(d)
+        # never smaller than the prior volume its points stand for (Feroz et al.
+        # 2009, section 5.1.1): an ellipsoid fitted to few points in many
+        # dimensions would otherwise cut into the iso-likelihood contour
+        if self.logvol < min_logvol:
+            self.L = self.L*math.exp((min_logvol - self.logvol)/d)
+            self.logvol = min_logvol
 
     def draw(self, n: int, rng) -> np.ndarray:
         z = rng.standard_normal((n, self.d))
@@ -154,28 +160,41 @@ def _kmeans2(pts: np.ndarray, rng, iters: int = 20):
 
 
 class _Bound:
-    """Union of one or two ellipsoids, intersected with the unit cube.  Uniform
-    sampling from a union: pick an ellipsoid by volume, draw, and accept with
-    probability 1 / (number of ellipsoids containing the point)."""
+    """Union of ellipsoids, intersected with the unit cube.  The live points are
+    partitioned recursively by 2-means, as MultiNest does; a split is kept
+    when the two enlarged ellipsoids together have clearly less volume than
+    the one around all the points.  Uniform sampling from the union: pick an
+    ellipsoid by volume, draw in it, and accept with probability
+    1 / (number of ellipsoids containing the point)."""
 
-    def __init__(self, pts: np.ndarray, enlarge: float, rng, split: bool):
-        d = pts.shape[1]
-        one = _Ellipsoid(pts, enlarge)
-        self.ells = [one]
-        if split and pts.shape[0] >= 4*(d + 1):
-            lab = _kmeans2(pts, rng)
-            if lab is not None and min(lab.sum(), (~lab).sum()) >= 2*(d + 1):
-                a, b = _Ellipsoid(pts[~lab], enlarge), _Ellipsoid(pts[lab], enlarge)
-                # split only if it pays clearly (MultiNest: total volume shrinks)
-                if np.logaddexp(a.logvol, b.logvol) < one.logvol + math.log(0.5):
-                    self.ells = [a, b]
+    def __init__(self, pts: np.ndarray, enlarge: float, rng, split: bool, logx: float = 0.0, max_ellipsoids: int = 16):
+        n, d = pts.shape
+        self.d = d
+        self.ells = []
+        min_pts = 2*(d + 1)
+
+        def ell(p):
+            # expected prior volume of the region these points sample: X n_k / N
+            return _Ellipsoid(p, enlarge, logx + math.log(p.shape[0]/n) + math.log(enlarge))
+
+        def build(p, e):
+            if split and len(self.ells) + 1 < max_ellipsoids and p.shape[0] >= 2*min_pts:
+                lab = _kmeans2(p, rng)
+                if lab is not None and min(int(lab.sum()), int((~lab).sum())) >= min_pts:
+                    a, b = ell(p[~lab]), ell(p[lab])
+                    if np.logaddexp(a.logvol, b.logvol) < e.logvol + math.log(0.5):
+                        build(p[~lab], a)
+                        build(p[lab], b)
+                        return
+            self.ells.append(e)
+
+        build(pts, ell(pts))
         lv = np.array([e.logvol for e in self.ells])
         self.logvol = float(np.logaddexp.reduce(lv))
         self.p = np.exp(lv - self.logvol)
-        self.d = d
 
-    def draw(self, n: int, rng, max_tries: int = 200) -> np.ndarray:
-        """n points uniform in (union of ellipsoids) x [0,1]^d."""
+    def draw(self, n: int, rng, max_tries: int = 400) -> np.ndarray:
+        """n points uniform in (union of ellipsoids) x [0,1)^d."""
         out = np.empty((0, self.d))
         want = n
         for _ in range(max_tries):
@@ -183,16 +202,22 @@ class _Bound:
             if len(self.ells) == 1:
                 u = self.ells[0].draw(m, rng)
             else:
-                which = rng.random(m) < self.p[1]
-                u = np.where(which[:, None], self.ells[1].draw(m, rng), self.ells[0].draw(m, rng))
-                k = self.ells[0].contains(u).astype(int) + self.ells[1].contains(u).astype(int)
-                u = u[rng.random(m)*np.maximum(k, 1) < 1.0]
+                which = rng.choice(len(self.ells), size=m, p=self.p)
+                u = np.empty((m, self.d))
+                for k, e in enumerate(self.ells):
+                    sel = which == k
+                    if sel.any():
+                        u[sel] = e.draw(int(sel.sum()), rng)
+                cnt = np.zeros(m, int)
+                for e in self.ells:
+                    cnt += e.contains(u)
+                u = u[rng.random(m)*np.maximum(cnt, 1) < 1.0]
             u = u[np.all((u >= 0.0) & (u < 1.0), axis=1)]
             out = np.concatenate([out, u[:want]])
             want = n - out.shape[0]
             if want <= 0:
                 return out
-        raise RuntimeError("nested sampling: the bounding ellipsoid lies almost entirely outside the unit cube")
+        raise RuntimeError("nested sampling: the bounding ellipsoids lie almost entirely outside the unit cube")
 
 
 def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int, *, nlive: int = 300,
@@ -265,7 +290,7 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     while not done:
         # bound from the current live points; while it is no smaller than the
         # cube itself, draw from the cube
-        bound = _Bound(live_u, enlarge, rng, split)
+        bound = _Bound(live_u, enlarge, rng, split, logx)
         if bound.logvol >= 0.0:
             cand = rng.random((batch, ndims))
         else:
@@ -274,7 +299,10 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         nevals += batch
         nbatches += 1
         proposed += batch
-        for u, ll in zip(cand, cl):
+        # the threshold only rises during the step: candidates at or below the
+        # threshold it starts with can never be accepted
+        for k in np.nonzero(cl > live_l.min())[0]:
+            u, ll = cand[k], cl[k]
             worst = int(np.argmin(live_l))
             lmin = live_l[worst]
             if not ll > lmin:
@@ -331,8 +359,7 @@ def run(like, *, nlive: int = 300, batch: int = 64, tol: float = 0.1, eff: float
     ev = evaluate if evaluate is not None else like.model.loglike_batch
 
     def lb(cubes: np.ndarray) -> np.ndarray:
-        P = np.stack([like.device_params(like.physical(c)) for c in cubes])
-        return np.asarray(ev(P), dtype=np.float64)
+        return np.asarray(ev(like.device_params_batch(like.physical_batch(cubes))), dtype=np.float64)
 
     return nested_sample(lb, like.ndims, nlive=nlive, batch=batch, tol=tol, eff=eff, seed=seed, maxiter=maxiter,
                          transform=like.physical, **kw)
