@@ -57,8 +57,10 @@ def test_two_modes_are_both_found():
 
     def lb(u):
         return np.logaddexp(f1(u), f2(u)) - math.log(2)
-    r = S.nested_sample(lb, 2, nlive=400, batch=64, seed=5)
+    r = S.nested_sample(lb, 2, nlive=400, batch=64, seed=5, split=True)
     assert abs(r.logz) < 4*r.logz_err + 0.05
+    r1 = S.nested_sample(lb, 2, nlive=400, batch=64, seed=5)           # one ellipsoid: same answer, more evaluations
+    assert abs(r1.logz) < 4*r1.logz_err + 0.05 and r1.nevals > r.nevals
     w = r.weights
     left = w[r.samples[:, 0] < 0.5].sum()
     assert 0.35 < left < 0.65
@@ -152,3 +154,16 @@ def test_sampler_on_a_lens_model(gpu_ctx):
     assert np.all(np.abs(mean - 0.5) < 5*std + 0.02), (mean, std)
     assert np.all(std < 0.2)
     assert r.nevals == 100 + 50*(r.nbatches - 2)
+
+
+def test_posterior_in_a_corner_of_the_prior():
+    """A likelihood peaked at a corner of the unit cube in 8 dimensions: almost
+    all of a bounding ellipsoid lies outside the cube; draws fall back to the
+    box around the live points."""
+    sig = 0.01
+
+    def lb(u):
+        return -0.5*((u/sig)**2).sum(axis=1)
+    r = S.nested_sample(lb, 8, nlive=100, batch=64, seed=3, tol=0.5)
+    z = 8*math.log(sig*math.sqrt(math.pi/2))           # half a Gaussian per dimension
+    assert abs(r.logz - z) < 5*r.logz_err + 0.1, (r.logz, z)
