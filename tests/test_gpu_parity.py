@@ -483,3 +483,29 @@ def test_device_data_preparation(gpu_ctx):
     assert np.array_equal(m.weight_map(), w2)
     with pytest.raises(ValueError):
         m.set_data(image=np.zeros((3, 3), np.float32))
+
+
+@pytest.mark.parametrize("flags", MATH_MODES)
+def test_two_rays_per_thread_underflow(gpu_ctx, monkeypatch, flags):
+    """Far wings of compact sources without sky: brightness runs through the
+    smallest normal numbers into underflow.  The scalar build flushes denormals
+    at every operation, the packed multiply leaves that to its consumer: the
+    images must still agree -- bit for bit wherever the value is a normal
+    number, and to within the smallest normal number elsewhere."""
+    import lensed_b200 as L
+    monkeypatch.setenv("LCU_SPLIT", "1")
+    img = np.zeros((96, 96), np.float32)
+    for objects, params in (
+            (["gauss"], [48.3, 47.6, 1.1, -12.0, 0.8, 20.0]),
+            (["sie", "gauss", "exponential"], [48.5, 48.5, 15.0, 0.7, 30.0, 50.0, 47.0, 0.9, -9.0, 0.9, 10.0,
+                                                46.0, 50.0, 0.35, -8.0, 0.8, 70.0]),
+            (["sersic", "sersic"], [48.2, 48.9, 0.8, -10.0, 0.5, 0.9, 40.0, 60.0, 30.0, 0.3, -6.0, 0.8, 0.7, 100.0])):
+        params = np.array(params, np.float32)
+        cfg = H.Config("underflow", objects, params, img, np.ones_like(img), rule="sub2")
+        a = cfg.product(gpu_ctx, flags=flags).render(params)["raw"]
+        b = cfg.product(gpu_ctx, flags=flags | L.LCU_NO_PAIR).render(params)["raw"]
+        tiny = np.float32(1.1754944e-38)
+        assert (b == 0).any() or (np.abs(b) < 1e-30).any(), f"{objects}: the scene does not reach underflow"
+        normal = np.abs(b) >= tiny
+        assert np.array_equal(a[normal].view(np.uint32), b[normal].view(np.uint32)), objects
+        assert np.all(np.abs(a[~normal].astype(np.float64) - b[~normal]) <= tiny), objects
