@@ -19,6 +19,12 @@ points of one step are drawn *before* any of them is evaluated:
         if L(c) > L_min(live): the worst live point dies (weight L_min dX),
                                c takes its place, X shrinks by exp(-1/nlive)
 
+When rejection from the bound stops paying (curved posteriors in >~ 10
+dimensions: acceptance ~1e-3), the candidates of a round come from constrained
+random walks instead -- copies of live points take Metropolis steps inside the
+current contour, all walkers advancing by one step per launch -- and are played
+against the live set in the same way.
+
 Every candidate is an independent uniform draw from a region that contains the
 whole iso-likelihood contour of every threshold met during the step (contours
 only shrink), so a candidate accepted against the threshold current at its turn
@@ -239,6 +245,7 @@ def _box_draw(pts: np.ndarray, n: int, enlarge: float, rng) -> np.ndarray:
 def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int, *, nlive: int = 300,
                   batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0, maxiter: int = 0,
                   transform: Optional[Callable[[np.ndarray], np.ndarray]] = None, split: bool = False,
+                  method: str = "auto", walks: int = 0,
                   callback: Optional[Callable[[dict], None]] = None, update_interval: int = 0) -> NestedResult:
     """Nested sampling of a likelihood over the unit cube [0,1)^ndims.
 
@@ -250,6 +257,20 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     tol           : stop when the live points can raise ln Z by less than this
     eff           : target efficiency; the bound's volume is enlarged by 1/eff
     maxiter       : stop after this many dead points (0 = no limit)
+    method        : how new points are drawn inside the likelihood contour.
+                    "reject": uniform draws from the ellipsoidal bound (exact, but the
+                    acceptance falls to 1e-3 and below for curved posteriors in >~ 10
+                    dimensions); "rwalk": ``walks`` Metropolis steps from copies of live
+                    points, constrained to the contour, proposals shaped by the live
+                    points' covariance -- one launch per step for all walkers of a
+                    round (Skilling 2006; cost ~ walks evaluations per dead point in
+                    any dimension); "auto" (default): rejection while more than one
+                    candidate in ``walks`` is accepted, random walks from then on
+    walks         : Metropolis steps per new point for "rwalk"; 0 = max(25, 8 ndims).  Too few
+                    steps leave new points correlated with their starting points and
+                    bias ln Z upwards (12-D test with a known answer: +0.5 at 25 steps,
+                    +0.14 +- 0.07 at 100, against a statistical error of 0.33); the
+                    posterior itself is far less sensitive
     split         : partition the live points into several ellipsoids.  Pays for
                     separated modes and curved degeneracies in few dimensions;
                     with ~nlive/10 points per ellipsoid in >~ 10 dimensions the
@@ -260,6 +281,10 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         raise ValueError("nested_sample: need ndims >= 1, nlive >= 2, batch >= 1")
     if not 0.0 < eff <= 1.0:
         raise ValueError("nested_sample: eff must be in (0, 1]")
+    if method not in ("auto", "reject", "rwalk") or walks < 0:
+        raise ValueError("nested_sample: method must be 'auto', 'reject' or 'rwalk', walks >= 0")
+    if walks == 0:
+        walks = max(25, 8*ndims)
     rng = np.random.default_rng(seed)
 
     nan_points = 0
@@ -307,23 +332,72 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         h = t_new + t_old - new
         logz = new
 
+    use_walk = method == "rwalk"
+    recent = []                                  # acceptance of the last rejection steps
+    step_scale = 1.0                             # random-walk step, in units of the live covariance
+    walk_rounds = walk_accept = 0
+
+    def walk_round():
+        """One round of constrained random walks: `walkers` copies of live points
+        take `walks` Metropolis steps inside {L > L_min at the start of the
+        round}; every step is one launch over all walkers.  Returns the end
+        points that moved (a walker that never moved is a copy of a live point
+        and is dropped)."""
+        nonlocal nevals, nbatches, step_scale, walk_accept
+        nw = max(1, min(batch, nlive//2))
+        lmin0 = live_l.min()
+        start = rng.integers(nlive, size=nw)
+        u, ll = live_u[start].copy(), live_l[start].copy()
+        cov = np.cov(live_u, rowvar=False).reshape(ndims, ndims)
+        w, v = np.linalg.eigh(cov)
+        w = np.maximum(w, max(w.max(), 1e-300)*1e-12)
+        chol = np.linalg.cholesky((v*w) @ v.T)
+        moved = np.zeros(nw, bool)
+        nacc = 0
+        for _ in range(walks):
+            prop = u + step_scale*(rng.standard_normal((nw, ndims)) @ chol.T)
+            inside = np.all((prop >= 0.0) & (prop < 1.0), axis=1)
+            if inside.any():
+                lp = evaluate(prop[inside])
+                nevals += int(inside.sum())
+                nbatches += 1
+                ok = np.zeros(nw, bool)
+                ok[inside] = lp > lmin0
+                full = np.empty(nw)
+                full[inside] = lp
+                u[ok], ll[ok] = prop[ok], full[ok]
+                moved |= ok
+                nacc += int(ok.sum())
+        # step size towards ~40 % acceptance (the usual target for constrained walks)
+        rate = nacc/(nw*walks)
+        step_scale *= math.exp((rate - 0.4)/2.0)
+        step_scale = min(max(step_scale, 1e-6), 4.0)
+        walk_accept += nacc
+        return u[moved], ll[moved], nw*walks
+
     done = False
     while not done:
-        # bound from the current live points; while it is no smaller than the
-        # cube itself, draw from the cube
-        bound = _Bound(live_u, enlarge, rng, split, logx)
-        if bound.logvol >= 0.0:
-            cand = rng.random((batch, ndims))
+        if use_walk:
+            cand, cl, cost = walk_round()
+            walk_rounds += 1
+            proposed += cost
         else:
-            try:
-                cand = bound.draw(batch, rng)
-            except RuntimeError:
-                # posterior pressed into a corner of the prior in many dimensions
-                cand = _box_draw(live_u, batch, enlarge, rng)
-        cl = evaluate(cand)
-        nevals += batch
-        nbatches += 1
-        proposed += batch
+            # bound from the current live points; while it is no smaller than the
+            # cube itself, draw from the cube
+            bound = _Bound(live_u, enlarge, rng, split, logx)
+            if bound.logvol >= 0.0:
+                cand = rng.random((batch, ndims))
+            else:
+                try:
+                    cand = bound.draw(batch, rng)
+                except RuntimeError:
+                    # posterior pressed into a corner of the prior in many dimensions
+                    cand = _box_draw(live_u, batch, enlarge, rng)
+            cl = evaluate(cand)
+            nevals += batch
+            nbatches += 1
+            proposed += batch
+        before = accepted
         # the threshold only rises during the step: candidates at or below the
         # threshold it starts with can never be accepted
         for k in np.nonzero(cl > live_l.min())[0]:
@@ -351,6 +425,11 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
             if maxiter and niter >= maxiter:
                 done = True
                 break
+        if not use_walk and method == "auto":
+            recent.append((accepted - before)/batch)
+            recent = recent[-8:]
+            if len(recent) == 8 and sum(recent)/8 < 1.0/walks:
+                use_walk = True
         if callback is not None and (update_interval <= 0 or nbatches % update_interval == 0 or done):
             callback(dict(niter=niter, nevals=nevals, nbatches=nbatches, logz=logz, logx=logx,
                           lmax=float(live_l.max()), efficiency=accepted/max(proposed, 1)))
@@ -370,7 +449,9 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     phys = np.stack([np.asarray(transform(s), dtype=np.float64) for s in samples]) if transform is not None else None
     return NestedResult(logz=logz, logz_err=math.sqrt(max(h, 0.0)/nlive), information=h, samples=samples, physical=phys,
                         loglike=ll, logwt=logwt, niter=niter, nevals=nevals, nbatches=nbatches,
-                        efficiency=accepted/max(proposed, 1), stats={"nan_points": nan_points})
+                        efficiency=accepted/max(proposed, 1),
+                        stats={"nan_points": nan_points, "walk_rounds": walk_rounds, "walk_step": step_scale,
+                               "walk_acceptance": walk_accept/max(walk_rounds*walks*max(1, min(batch, nlive//2)), 1)})
 
 
 def run(like, *, nlive: int = 300, batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0,

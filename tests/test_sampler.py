@@ -167,3 +167,31 @@ def test_posterior_in_a_corner_of_the_prior():
     r = S.nested_sample(lb, 8, nlive=100, batch=64, seed=3, tol=0.5)
     z = 8*math.log(sig*math.sqrt(math.pi/2))           # half a Gaussian per dimension
     assert abs(r.logz - z) < 5*r.logz_err + 0.1, (r.logz, z)
+
+
+def test_random_walks_take_over_when_rejection_stops_paying():
+    """Curved, badly scaled posterior in 8 dimensions (two Rosenbrock-like
+    pairs times a narrow Gaussian): rejection from one ellipsoid accepts a few
+    per mille; the default hands over to constrained random walks and gets the
+    evidence with a fraction of the evaluations."""
+    def banana(x, y):
+        X, Y = (x - 0.5)*6, (y - 0.3)*6
+        return -((1 - X)**2 + 10*(Y - X**2)**2)
+    g = np.linspace(0, 1, 1501)
+    G = (g[:-1] + g[1:])/2
+    XX, YY = np.meshgrid(G, G, indexing="ij")
+    z2 = math.log(np.exp(banana(XX, YY)).mean())
+    sig = np.array([0.002, 0.01, 0.003, 0.03])
+
+    def lb(u):
+        return (banana(u[:, 0], u[:, 1]) + banana(u[:, 2], u[:, 3]) - 0.5*(((u[:, 4:] - 0.5)/sig)**2).sum(axis=1)
+                - np.log(sig*math.sqrt(2*math.pi)).sum())
+    r = S.nested_sample(lb, 8, nlive=300, batch=128, seed=2)
+    assert r.stats["walk_rounds"] > 0 and 0.2 < r.stats["walk_acceptance"] < 0.6
+    assert abs(r.logz - 2*z2) < 3*r.logz_err + 0.1, (r.logz, 2*z2, r.logz_err)
+    assert np.allclose(r.mean()[4:], 0.5, atol=3*sig.max()/10 + 5e-3)
+    assert r.efficiency > 0.005
+    e = S.nested_sample(lb, 8, nlive=300, batch=128, seed=2, method="reject", maxiter=3000)
+    assert e.stats["walk_rounds"] == 0
+    w = S.nested_sample(lb, 8, nlive=300, batch=128, seed=2, method="rwalk", walks=40, maxiter=3000)
+    assert w.stats["walk_rounds"] > 0 and w.niter == e.niter == 3000
