@@ -132,7 +132,9 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 
     if(S == 1)
     {
-        if(live)
+        // no branch on `live` around the loop: threads past the end of the range
+        // shoot the rays of pixel k0 and drop the result, the loop stays in
+        // uniform control flow and the object block in uniform registers
         {
 #if LCU_QUAD_NI > 0
             // Cartesian rule (first axis outer, second inner, as the tables
@@ -287,8 +289,10 @@ __device__ __forceinline__ void lcu_render_pair_impl(const lcu_render_args& a)
     const lcu_pf2 x(lcu_pf(a.pcs.x) + lcu_pf(a.pcs.z)*px, lcu_pf(a.pcs.y) + lcu_pf(a.pcs.w)*py);
 
     // value and error of quadrature, kernel/lensed.cl:27-32
+    // (threads past the end of the range shoot the rays of pixel k0 and drop the
+    // result: no divergent branch around the loop, so that the compiler can keep
+    // the object block in uniform registers)
     lcu_pf f0 = 0.0f, f1 = 0.0f;
-    if(live0)
     {
 #if LCU_QUAD_NI > 0
 #pragma unroll 1

@@ -509,3 +509,20 @@ def test_two_rays_per_thread_underflow(gpu_ctx, monkeypatch, flags):
         normal = np.abs(b) >= tiny
         assert np.array_equal(a[normal].view(np.uint32), b[normal].view(np.uint32)), objects
         assert np.all(np.abs(a[~normal].astype(np.float64) - b[~normal]) <= tiny), objects
+
+
+def test_fma_contraction_flag(gpu_ctx, monkeypatch):
+    """LCU_FAST_MATH (FMA contraction, what -cl-fast-relaxed-math allows the
+    reference's compiler) is opt-in: it stays close to the strict result but
+    is not held to the 1e-5 bar.  Both render kernels
+    honour it: the packed multiply is then issued with .ftz, which lets ptxas
+    contract it into FFMA2."""
+    import lensed_b200 as L
+    monkeypatch.setenv("LCU_SPLIT", "1")
+    cfg = H.synthetic_config("c4", 128)
+    strict = cfg.product(gpu_ctx).render(cfg.params)["raw"]
+    for extra in (0, L.LCU_NO_PAIR):
+        m = cfg.product(gpu_ctx, flags=L.LCU_FAST_MATH | extra)
+        r = H.rel_err(m.render(cfg.params)["raw"], strict)
+        assert 0 < r.max() <= 1e-4 and np.quantile(r, 0.999) <= 2e-5, (extra, r.max())
+    assert cfg.product(gpu_ctx, flags=L.LCU_FAST_MATH).rays_per_thread == 2

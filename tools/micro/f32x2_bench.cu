@@ -12,6 +12,8 @@ __device__ __forceinline__ float fma1(float a, float b, float c){ float r; asm v
 __device__ __forceinline__ float mul1(float a, float b){ float r; asm volatile("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float add1(float a, float b){ float r; asm volatile("add.rn.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float ex2(float a){ float r; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float rcpa(float a){ float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float lg2a(float a){ float r; asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ u64 pk(float a, float b){ u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float lo(u64 a){ float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x; }
 __device__ __forceinline__ float hi(u64 a){ float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return y; }
@@ -24,10 +26,13 @@ __device__ __forceinline__ float hi(u64 a){ float x, y; asm("mov.b64 {%0,%1}, %2
 //      6: scalar 16 FFMA + 8 IADD/LOP  7: 8 FFMA2 + 8 IADD/LOP
 //      8: FMUL2 x8   9: FADD2 x8   10: FFMA2 x8 + scalar FFMA x8   11: FFMA2 x8 + scalar FMUL x8
 //      12: FMUL2 x8 + scalar FFMA x8  13: scalar FFMA x8   14: scalar FMUL x8
+//      15: MUFU.EX2 x8   16: MUFU.RCP x8   17: MUFU.EX2 x8 + 16 ALU   18: MUFU.EX2 x8 + scalar FFMA x16
+//      19: MUFU.EX2 x8 + FFMA2 x8   20: MUFU.EX2 x4 + MUFU.LG2 x4
 // (the packed multiply is issued without .ftz: ptxas 12.9 contracts mul.ftz.f32x2 + add.ftz.f32x2 into FFMA2)
 template<int MODE> __global__ void __launch_bounds__(256) kern(float* out, float s, float t)
 {
-    float a[2*N]; u64 p[N]; float m[4]; unsigned q[4];
+    float a[2*N]; u64 p[N]; float m[4]; unsigned q[4]; float mm[8];
+    for(int i = 0; i < 8; ++i) mm[i] = 0.3f + i*0.01f + threadIdx.x*1e-4f;
     for(int i = 0; i < 2*N; ++i) a[i] = threadIdx.x*1e-3f + i;
     for(int i = 0; i < N; ++i) p[i] = pk(a[2*i], a[2*i+1]);
     for(int i = 0; i < 4; ++i) { m[i] = i*0.1f + threadIdx.x*1e-4f; q[i] = threadIdx.x + i; }
@@ -71,6 +76,30 @@ template<int MODE> __global__ void __launch_bounds__(256) kern(float* out, float
 #pragma unroll
             for(int i = 0; i < 4; ++i) m[i] = ex2(m[i]);
         }
+        if(MODE == 15 || MODE == 17 || MODE == 18 || MODE == 19) {
+#pragma unroll
+            for(int i = 0; i < 8; ++i) mm[i] = ex2(mm[i]);
+        }
+        if(MODE == 16) {
+#pragma unroll
+            for(int i = 0; i < 8; ++i) mm[i] = rcpa(mm[i]);
+        }
+        if(MODE == 20) {
+#pragma unroll
+            for(int i = 0; i < 4; ++i) { mm[i] = ex2(mm[i]); mm[i+4] = lg2a(mm[i+4]); }
+        }
+        if(MODE == 18) {
+#pragma unroll
+            for(int i = 0; i < 2*N; ++i) a[i] = fma1(a[i], s, t);
+        }
+        if(MODE == 19) {
+#pragma unroll
+            for(int i = 0; i < N; ++i) p[i] = fma2(p[i], ss, tt);
+        }
+        if(MODE == 17) {
+#pragma unroll
+            for(int i = 0; i < 4; ++i) { q[i] = (q[i] + 0x3f2aaaabu) & 0xff800fffu; q[i] ^= q[(i+1)&3] >> 3; q[i] = (q[i] + 0x3f2aaaabu) & 0xff800fffu; q[i] ^= q[(i+2)&3] >> 5; }
+        }
         if(MODE == 6 || MODE == 7) {
 #pragma unroll
             for(int i = 0; i < 4; ++i) { q[i] = (q[i] + 0x3f2aaaabu) & 0xff800fffu; q[i] ^= q[(i+1)&3] >> 3; }
@@ -80,6 +109,7 @@ template<int MODE> __global__ void __launch_bounds__(256) kern(float* out, float
     for(int i = 0; i < 2*N; ++i) r += a[i];
     for(int i = 0; i < N; ++i) r += lo(p[i]) + hi(p[i]);
     for(int i = 0; i < 4; ++i) r += m[i] + q[i];
+    for(int i = 0; i < 8; ++i) r += mm[i];
     out[blockIdx.x*blockDim.x + threadIdx.x] = r;
 }
 
@@ -123,6 +153,12 @@ int main()
     run<11>("FFMA2 x8 + scalar FMUL x8", out, 24, 0);
     run<12>("FMUL2 x8 + scalar FFMA x8", out, 24, 0);
     run<0>("scalar FFMA x16 (again)", out, 16, 0);
+    run<15>("MUFU.EX2 x8", out, 0, 8);
+    run<16>("MUFU.RCP x8", out, 0, 8);
+    run<20>("MUFU.EX2 x4 + LG2 x4", out, 0, 8);
+    run<17>("MUFU.EX2 x8 + 16 ALU", out, 0, 24);
+    run<18>("MUFU.EX2 x8 + scalar FFMA x16", out, 16, 8);
+    run<19>("MUFU.EX2 x8 + FFMA2 x8", out, 16, 8);
     cudaError_t e = cudaDeviceSynchronize(); printf("status %s\n", cudaGetErrorString(e));
     return 0;
 }
