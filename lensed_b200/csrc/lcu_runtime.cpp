@@ -314,16 +314,19 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         void* args[] = { &B, (void*)&d_params, &m->d_objs };
         int rc = launch(m, m->f_set, dim3((unsigned)div_up(nb, 64)), dim3(64), args, st);
         if(rc) return rc;
-        if(m->obj_const)
-            RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m->c_objs), m->d_objs,
-                                     nb*m->words*sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
-    if(ev) cudaEventRecord(ev[1], st);
 
     size_t r0, r1;
     render_rows(m, &r0, &r1);
     const size_t nk = (r1 - r0)*m->width;
     const int ngroups = (int)group_count(m);
+    const int split = pick_split(m, nk, nb);
+    // the large-image kernels read the object blocks from the constant bank;
+    // the split kernels (small images) take them from global memory themselves
+    if(m->obj_const && split == 1)
+        RT_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(m->c_objs), m->d_objs,
+                                 nb*m->words*sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if(ev) cudaEventRecord(ev[1], st);
 
     // render, src/nested.c:84
     {
@@ -347,7 +350,6 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
             if(want_chi2) a.mode |= OUT_CHI2;
             if(a.chimap) a.mode |= OUT_CHIMAP;
         }
-        const int split = pick_split(m, nk, nb);
         const int idx = split == 1 ? 0 : split == 2 ? 1 : split == 4 ? 2 : 3;
         void* args[] = { &a };
         int rc;
@@ -475,9 +477,26 @@ bool single_point_graph(lcu_model* m)
     bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if(ok)
     {
-        ok = cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
-        ok = ok && enqueue_batch(m, 1, m->d_params, m->d_lnew, m->stream) == LCU_OK;
-        ok = ok && cudaMemcpyAsync(m->h_lnew, m->d_lnew, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+        // The pinned staging buffers are mapped into the device's address space
+        // (unified addressing): set_params reads the point's few parameters straight
+        // from host memory and the reduction writes the result there, which takes
+        // the two copy nodes (and their dependencies) out of the graph.  LCU_GRAPH_COPIES
+        // restores them.
+        float* dp = nullptr;
+        double* dl = nullptr;
+        const bool mapped = !getenv("LCU_GRAPH_COPIES")
+            && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), m->h_params, 0) == cudaSuccess
+            && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dl), m->h_lnew, 0) == cudaSuccess && dp && dl;
+        if(!mapped)
+            cudaGetLastError();
+        if(mapped)
+            ok = enqueue_batch(m, 1, dp, dl, m->stream) == LCU_OK;
+        else
+        {
+            ok = cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
+            ok = ok && enqueue_batch(m, 1, m->d_params, m->d_lnew, m->stream) == LCU_OK;
+            ok = ok && cudaMemcpyAsync(m->h_lnew, m->d_lnew, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+        }
         ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
     }
     if(ok)

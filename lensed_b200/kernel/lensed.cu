@@ -111,15 +111,24 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     const bool live = kk < a.nk;
     const long long k = a.k0 + (live ? kk : 0);
 
+    // Object block of this point: constant bank for the large-image kernel
+    // (S = 1; the host copies the blocks there between set_params and render),
+    // shared memory, filled from set_params' output in global memory, for the
+    // split kernels -- those run on small images, where the extra copy node
+    // would cost more than the block's 48 loads (single-point latency)
+    const uint* data;
 #if LCU_OBJ_CONST
-    const uint* data = reinterpret_cast<const uint*>(lcu_objs_c) + b*LCU_WORDS;
-#else
-    __shared__ __align__(16) uint sdata[LCU_WORDS];
-    for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
-        sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
-    __syncthreads();
-    const uint* data = sdata;
+    if constexpr(S == 1)
+        data = reinterpret_cast<const uint*>(lcu_objs_c) + b*LCU_WORDS;
+    else
 #endif
+    {
+        __shared__ __align__(16) uint sdata[LCU_WORDS];
+        for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+            sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
+        __syncthreads();
+        data = sdata;
+    }
 
     // pixel position, kernel/lensed.cl:24
     const float px = (float)(k % IMAGE_WIDTH);
