@@ -29,6 +29,13 @@ static int meta(void)
         int type; size_t words, npar;
         lcu_param pars[16];
         CHECK(lcu_object_info(ctx, OBJECTS[i], &type, &words, &npar, pars, 16));
+        const char* why = NULL;
+        const int pair = lcu_object_pairable(ctx, OBJECTS[i], &why);
+        if(pair != 1)
+        {
+            fprintf(stderr, "%s does not compile for two rays per thread: %s\n", OBJECTS[i], why ? why : "?");
+            return 1;
+        }
         printf("object %s %c %zu %zu", OBJECTS[i], type, words, npar);
         for(size_t j = 0; j < npar; ++j)
             printf(" %s:%d:%g:%g:%d", pars[j].name, pars[j].type, pars[j].bounds[0], pars[j].bounds[1],
@@ -99,6 +106,23 @@ static int loglike(int device, size_t size)
     for(size_t i = 0; i < size*size; ++i)
         sum += img[i];
     printf("flux %.9g launches %llu\n", sum, lcu_launch_count());
+
+    /* data preparation on the device: weight = gain/(image + offset), one masked pixel;
+       then the same evaluation against the new map */
+    {
+        int* mask = calloc(size*size, sizeof(int));
+        float* w2 = malloc(size*size*sizeof(float));
+        double again;
+        mask[size + 1] = 1;
+        CHECK(lcu_model_make_weight(model, NULL, 1800.f, 2.9633, mask));
+        CHECK(lcu_model_get_weight(model, w2));
+        CHECK(lcu_loglike(model, params[0], &again));
+        printf("prep %d %.9g %.9g %.17g\n", lcu_model_rays_per_thread(model), w2[0], w2[size + 1], again);
+        CHECK(lcu_model_set_data(model, NULL, weight));
+        CHECK(lcu_loglike(model, params[0], &again));
+        printf("back %.17g\n", again);
+        free(mask); free(w2);
+    }
 
     lcu_model_destroy(model);
     lcu_destroy(ctx);

@@ -59,3 +59,9 @@ def test_loglike_from_c(host_check):
         assert abs(lnew[1 + b] - ref) <= 3e-6*abs(ref), (b, lnew[1 + b], ref)
     flux = float(out[2].split()[1])
     assert flux > 0 and int(out[2].split()[3]) > 0
+    # device-side weight map (image is all zeros here: gain/offset everywhere, 0 at the masked pixel)
+    prep = out[3].split()
+    assert prep[0] == "prep" and int(prep[1]) == 2
+    assert np.float32(float(prep[2])) == np.float32(np.float32(1800.0)/np.float64(2.9633)) and float(prep[3]) == 0.0
+    assert float(prep[4]) != lnew[0]
+    assert out[4].split()[0] == "back" and float(out[4].split()[1]) == lnew[0]          # original weights restored
