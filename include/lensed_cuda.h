@@ -182,6 +182,9 @@ const char* lcu_model_source(const lcu_model* model);
 const char* lcu_model_build_log(const lcu_model* model);
 /* compiled sm_100a module image (for cuobjdump / caching); returns its size */
 size_t lcu_model_cubin(const lcu_model* model, const void** image);
+/* registers per thread and stack (spill) bytes of one kernel of the module, e.g.
+   "lcu_render_pair", read from the module image; LCU_E_ARG if there is no such kernel */
+int lcu_model_kernel_usage(const lcu_model* model, const char* kernel, unsigned* registers, unsigned* stack_bytes);
 
 /*
  * Restrict the model to the image rows [row0, row1) (multi-GPU row strips):

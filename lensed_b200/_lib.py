@@ -71,6 +71,7 @@ SYMBOLS = {
     "lcu_model_source": (C.c_char_p, [C.c_void_p]),
     "lcu_model_build_log": (C.c_char_p, [C.c_void_p]),
     "lcu_model_cubin": (C.c_size_t, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "lcu_model_kernel_usage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "lcu_model_set_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "lcu_model_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcu_model_make_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_void_p]),

@@ -206,6 +206,12 @@ class Model:
         n = lib.lcu_model_cubin(self._h, C.byref(img))
         return C.string_at(img, n)
 
+    def kernel_usage(self, kernel: str):
+        """(registers per thread, stack bytes) of a kernel of the compiled module."""
+        r, st = C.c_uint(), C.c_uint()
+        check(lib.lcu_model_kernel_usage(self._h, kernel.encode(), C.byref(r), C.byref(st)))
+        return int(r.value), int(st.value)
+
     def set_rows(self, row0: int, row1: int):
         check(lib.lcu_model_set_rows(self._h, int(row0), int(row1)))
 

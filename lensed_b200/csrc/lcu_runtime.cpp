@@ -1016,6 +1016,19 @@ size_t lcu_model_cubin(const lcu_model* m, const void** image)
     return m->cubin.size();
 }
 
+int lcu_model_kernel_usage(const lcu_model* m, const char* kernel, unsigned* registers, unsigned* stack_bytes)
+{
+    unsigned regs = 0, stack = 0;
+    if(!m || !kernel || !cubin_kernel_usage(m->cubin, kernel, &regs, &stack))
+    {
+        set_error("lcu_model_kernel_usage: no kernel \"%s\" in the module", kernel ? kernel : "(null)");
+        return LCU_E_ARG;
+    }
+    if(registers) *registers = regs;
+    if(stack_bytes) *stack_bytes = stack;
+    return LCU_OK;
+}
+
 int lcu_model_set_rows(lcu_model* m, size_t row0, size_t row1)
 {
     if(!m || row0 >= row1 || row1 > m->height)

@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 import lensed_b200 as L
 
@@ -117,3 +118,25 @@ def test_object_that_cannot_be_paired_falls_back(tmp_path):
         assert L.Model(ctx, ["sie", "sersic", "sky"], IMG, IMG).rays_per_thread == 2
     finally:
         ctx.close()
+
+
+def test_render_kernels_keep_the_object_block_out_of_vector_registers(compile_ctx):
+    """The ray loops run in uniform control flow, so ptxas holds the object
+    block (48 words for C4) in uniform registers: the two-rays kernel of the
+    1024^2 benchmark model needs ~44 vector registers and no stack.  A branch
+    on a per-thread condition around the loop would push it back to 80 (3
+    resident blocks instead of 5)."""
+    from lensed_b200 import workloads
+    w = workloads.c4(1024)
+    img = np.zeros((1024, 1024), np.float32)
+    for flags in (0, L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH):
+        m = L.Model(compile_ctx, w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=flags)
+        regs, stack = m.kernel_usage("lcu_render_pair")
+        assert regs <= 56 and stack == 0, (flags, regs, stack)
+        assert "LDCU" not in m.source          # (the source is CUDA C++; the property is ptxas's doing)
+    w5 = workloads.c5(4096)
+    m = L.Model(compile_ctx, w5["objects"], img, img, rule=w5["rule"], psf=w5["psf"], flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
+    regs, stack = m.kernel_usage("lcu_render_pair")
+    assert regs <= 85 and stack <= 64, (regs, stack)
+    with pytest.raises(L.LensedCudaError):
+        m.kernel_usage("no_such_kernel")

@@ -204,13 +204,19 @@ def test_row_strips_add_up(gpu_ctx):
         assert m.loglike(cfg.params) == full
 
 
-def test_shared_memory_object_blocks(gpu_ctx):
+def test_shared_memory_object_blocks(gpu_ctx, monkeypatch):
     import lensed_b200 as L
     cfg = H.synthetic_config("c4", 96)
     a = cfg.product(gpu_ctx)
     b = cfg.product(gpu_ctx, flags=L.LCU_OBJ_SHARED)
     P = H.workloads.param_batch(cfg.extra["workload"], 3)
-    assert np.array_equal(a.loglike_batch(P), b.loglike_batch(P))
+    base = a.loglike_batch(P)
+    assert np.array_equal(base, b.loglike_batch(P))
+    # the large-image kernels (two rays and one ray per thread) with the block in shared memory
+    monkeypatch.setenv("LCU_SPLIT", "1")
+    assert np.array_equal(base, b.loglike_batch(P))
+    c = cfg.product(gpu_ctx, flags=L.LCU_OBJ_SHARED | L.LCU_NO_PAIR)
+    assert np.array_equal(base, c.loglike_batch(P))
 
 
 def test_device_resident_batch(gpu_ctx):
