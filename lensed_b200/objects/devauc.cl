@@ -9,23 +9,11 @@
 
 type = SOURCE;
 
-params
-{
-    { "x",   POSITION_X },
-    { "y",   POSITION_Y },
-    { "r",   RADIUS     },
-    { "mag", MAGNITUDE  },
-    { "q",   AXIS_RATIO },
-    { "pa",  POS_ANGLE  },
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "mag", MAGNITUDE },
+        { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_profile;  // rotate by pa, squash first axis by q
-    float  scale;
-    float  peak;
-};
+// rotate by pa, squash first axis by q
+data { float2 centre; mat22 to_profile; float scale; float peak; };
 
 static float brightness(local data* this, float2 x)
 {
@@ -41,5 +29,7 @@ static void set(local data* this, float x, float y, float r, float mag, float q,
     this->centre     = (float2)(x, y);
     this->to_profile = (mat22)(q*cs, q*sn, -sn, cs);
     this->scale      = r;
-    this->peak       = exp(-0.4f*mag*LOG_10)/PI/r/r/q*DEVAUC_C;
+    // total flux of the r^(1/4) law: pi r^2 q I0 8!/b^8
+    float flux = exp(-0.4f*mag*LOG_10);
+    this->peak       = flux/PI/r/r/q*DEVAUC_C;
 }

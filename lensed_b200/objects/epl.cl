@@ -11,25 +11,11 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X              },
-    { "y",  POSITION_Y              },
-    { "r",  RADIUS                  },
-    { "t",  PARAMETER, { 0.f, 2.f } },
-    { "q",  AXIS_RATIO              },
-    { "pa", POS_ANGLE               }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS },
+        { "t", PARAMETER, { 0.f, 2.f } }, { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_lens;     // rotate, squash and scale into the elliptical frame
-    mat22  to_image;    // plain rotation back
-    float  slope;
-    float  flat;
-    float  amp;
-};
+// rotate, squash and scale into the elliptical frame; plain rotation back
+data { float2 centre; mat22 to_lens; mat22 to_image; float slope; float flat; float amp; };
 
 static float2 deflection(local data* this, float2 x)
 {

@@ -3,28 +3,11 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X              },
-    { "y",  POSITION_Y              },
-    { "r",  RADIUS                  },
-    { "t",  PARAMETER, { 0.f, 2.f } },
-    { "q",  AXIS_RATIO              },
-    { "pa", POS_ANGLE               },
-    { "g1", PARAMETER               },
-    { "g2", PARAMETER               }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS },
+        { "t", PARAMETER, { 0.f, 2.f } }, { "q", AXIS_RATIO }, { "pa", POS_ANGLE },
+        { "g1", PARAMETER }, { "g2", PARAMETER } };
 
-data
-{
-    float2 centre;
-    mat22  to_lens;
-    mat22  to_image;
-    mat22  shear;
-    float  slope;
-    float  flat;
-    float  amp;
-};
+data { float2 centre; mat22 to_lens; mat22 to_image; mat22 shear; float slope; float flat; float amp; };
 
 static float2 deflection(local data* this, float2 x)
 {

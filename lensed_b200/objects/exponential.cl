@@ -5,23 +5,10 @@
 
 type = SOURCE;
 
-params
-{
-    { "x",   POSITION_X },
-    { "y",   POSITION_Y },
-    { "rs",  RADIUS     },
-    { "mag", MAGNITUDE  },
-    { "q",   AXIS_RATIO },
-    { "pa",  POS_ANGLE  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "rs", RADIUS }, { "mag", MAGNITUDE },
+        { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_profile;
-    float  scale;
-    float  peak;
-};
+data { float2 centre; mat22 to_profile; float scale; float peak; };
 
 static float brightness(local data* this, float2 x)
 {
@@ -37,5 +24,7 @@ static void set(local data* this, float x, float y, float rs, float mag, float q
     this->centre     = (float2)(x, y);
     this->to_profile = (mat22)(q*cs, q*sn, -sn, cs);
     this->scale      = rs;
-    this->peak       = exp(-0.4f*mag*LOG_10)*0.5f/PI/rs/rs/q;
+    // total flux of an elliptical exponential disc: 2 pi rs^2 q I0
+    float flux = exp(-0.4f*mag*LOG_10);
+    this->peak       = flux*0.5f/PI/rs/rs/q;
 }

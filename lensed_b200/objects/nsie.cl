@@ -6,26 +6,10 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X },
-    { "y",  POSITION_Y },
-    { "r",  RADIUS     },
-    { "rc", RADIUS     },
-    { "q",  AXIS_RATIO },
-    { "pa", POS_ANGLE  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "rc", RADIUS },
+        { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_lens;
-    mat22  to_image;
-    float  core;
-    float  q_sq;
-    float  ecc;
-    float  amp;
-};
+data { float2 centre; mat22 to_lens; mat22 to_image; float core; float q_sq; float ecc; float amp; };
 
 static float2 deflection(local data* this, float2 x)
 {

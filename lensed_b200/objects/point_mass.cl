@@ -4,18 +4,9 @@
 
 type = LENS;
 
-params
-{
-    { "x", POSITION_X },
-    { "y", POSITION_Y },
-    { "r", RADIUS     }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS } };
 
-data
-{
-    float2 centre;
-    float  einstein_sq;
-};
+data { float2 centre; float einstein_sq; };
 
 static float2 deflection(local data* this, float2 x)
 {

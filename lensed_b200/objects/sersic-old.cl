@@ -4,25 +4,10 @@
 
 type = SOURCE;
 
-params
-{
-    { "x",   POSITION_X },
-    { "y",   POSITION_Y },
-    { "r",   RADIUS     },
-    { "mag", MAGNITUDE  },
-    { "n",   PARAMETER, { 0.5f, 8.0f } },
-    { "q",   AXIS_RATIO },
-    { "pa",  POS_ANGLE  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "mag", MAGNITUDE },
+        { "n", PARAMETER, { 0.5f, 8.0f } }, { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_profile;
-    float  log0;
-    float  log1;
-    float  half_inv_n;
-};
+data { float2 centre; mat22 to_profile; float log0; float log1; float half_inv_n; };
 
 static float brightness(local data* this, float2 x)
 {

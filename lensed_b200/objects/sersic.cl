@@ -8,25 +8,11 @@
 
 type = SOURCE;
 
-params
-{
-    { "x",   POSITION_X },
-    { "y",   POSITION_Y },
-    { "r",   RADIUS     },
-    { "mag", MAGNITUDE  },
-    { "n",   PARAMETER, POS_BOUND },
-    { "q",   AXIS_RATIO },
-    { "pa",  POS_ANGLE  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "mag", MAGNITUDE },
+        { "n", PARAMETER, POS_BOUND }, { "q", AXIS_RATIO }, { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_profile;  // rotate by pa, scale axes by sqrt(q), 1/sqrt(q)
-    float  log0;        // log I0
-    float  log1;        // log b - log(r)/n
-    float  half_inv_n;  // 1/(2n)
-};
+// rotate by pa, scale axes by sqrt(q), 1/sqrt(q); log I0; log b - log(r)/n; 1/(2n)
+data { float2 centre; mat22 to_profile; float log0; float log1; float half_inv_n; };
 
 static float brightness(local data* this, float2 x)
 {

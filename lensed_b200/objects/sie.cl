@@ -9,24 +9,11 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X },
-    { "y",  POSITION_Y },
-    { "r",  RADIUS     },
-    { "q",  AXIS_RATIO },
-    { "pa", POS_ANGLE  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "q", AXIS_RATIO },
+        { "pa", POS_ANGLE } };
 
-data
-{
-    float2 centre;
-    mat22  to_lens;     // rotation into the lens frame
-    mat22  to_image;    // and back
-    float  q_sq;
-    float  ecc;         // e
-    float  amp;         // r sqrt(q)/e
-};
+// rotation into the lens frame; and back; e; r sqrt(q)/e
+data { float2 centre; mat22 to_lens; mat22 to_image; float q_sq; float ecc; float amp; };
 
 static float2 deflection(local data* this, float2 x)
 {

@@ -5,27 +5,10 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X },
-    { "y",  POSITION_Y },
-    { "r",  RADIUS     },
-    { "q",  AXIS_RATIO },
-    { "pa", POS_ANGLE  },
-    { "g1", PARAMETER  },
-    { "g2", PARAMETER  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "q", AXIS_RATIO },
+        { "pa", POS_ANGLE }, { "g1", PARAMETER }, { "g2", PARAMETER } };
 
-data
-{
-    float2 centre;
-    mat22  to_lens;
-    mat22  to_image;
-    mat22  shear;
-    float  q_sq;
-    float  ecc;
-    float  amp;
-};
+data { float2 centre; mat22 to_lens; mat22 to_image; mat22 shear; float q_sq; float ecc; float amp; };
 
 static float2 deflection(local data* this, float2 x)
 {

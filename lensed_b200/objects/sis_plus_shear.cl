@@ -4,22 +4,13 @@
 
 type = LENS;
 
-params
-{
-    { "x",  POSITION_X },
-    { "y",  POSITION_Y },
-    { "r",  RADIUS     },
-    { "g1", PARAMETER  },
-    { "g2", PARAMETER  }
-};
+params { { "x", POSITION_X }, { "y", POSITION_Y }, { "r", RADIUS }, { "g1", PARAMETER },
+        { "g2", PARAMETER } };
 
-data
-{
-    float2 centre;
-    mat22  shear;
-    float  einstein;
-};
+data { float2 centre; mat22 shear; float einstein; };
 
+// The shear matrix acts on the offset from the lens centre, not on the image
+// position: the external field vanishes at the centre of the sphere.
 static float2 deflection(local data* this, float2 x)
 {
     float2 u = x - this->centre;

@@ -5,18 +5,9 @@
 
 type = FOREGROUND;
 
-params
-{
-    { "bg" },
-    { "dx", PARAMETER, UNBOUNDED, -0.0f },
-    { "dy", PARAMETER, UNBOUNDED, -0.0f }
-};
+params { { "bg" }, { "dx", PARAMETER, UNBOUNDED, -0.0f }, { "dy", PARAMETER, UNBOUNDED, -0.0f } };
 
-data
-{
-    float  level;
-    float2 slope;
-};
+data { float level; float2 slope; };
 
 static float foreground(local data* this, float2 x)
 {
