@@ -157,7 +157,7 @@ struct lcu_model
 
     // device state
     CUmodule mod = nullptr;
-    CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_reduce = nullptr;
+    CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_conv_small = nullptr, f_reduce = nullptr;
     CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
     CUfunction f_make_weight = nullptr;
     bool pair = false;
@@ -178,7 +178,7 @@ struct lcu_model
     cudaGraphExec_t graph1 = nullptr;
     bool graph1_off = false;
     size_t graph1_rows[2] = { 0, 0 };
-    int graph1_split = 0;
+    int graph1_split = 0, graph1_conv = -1;
     // dumper buffers (one point), allocated on first lcu_render
     float *d_value1 = nullptr, *d_error1 = nullptr, *d_model1 = nullptr, *d_chi1 = nullptr;
     // profiling: one set of stage events per launched chunk, harvested lazily
@@ -383,8 +383,16 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         if(chimap) c.mode |= OUT_CHIMAP;
         if(want_chi2) c.mode |= OUT_CHI2;
         void* args[] = { &c };
-        int rc = launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 64), (unsigned)div_up(m->row1 - m->row0, m->conv_tile_h), (unsigned)nb),
-                        dim3(256), args, st);
+        // 64 x conv_tile_h tiles with register reuse; 32 x 8 tiles (same bits) when
+        // those would not give every SM a block (LCU_CONV_SMALL=0/1 forces the choice)
+        const size_t rows = m->row1 - m->row0;
+        const size_t big = div_up(m->width, 64)*div_up(rows, m->conv_tile_h)*nb;
+        const char* force = getenv("LCU_CONV_SMALL");
+        const bool small = force && *force ? *force == '1' : big < (size_t)std::max(m->ctx->sm_count, 1);
+        int rc = small
+            ? launch(m, m->f_conv_small, dim3((unsigned)div_up(m->width, 32), (unsigned)div_up(rows, 8), (unsigned)nb), dim3(256), args, st)
+            : launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 64), (unsigned)div_up(rows, m->conv_tile_h), (unsigned)nb),
+                     dim3(256), args, st);
         if(rc) return rc;
     }
     if(ev) cudaEventRecord(ev[3], st);
@@ -461,7 +469,10 @@ bool single_point_graph(lcu_model* m)
         return false;
     const char* forced = getenv("LCU_SPLIT");
     const int split = forced && *forced ? atoi(forced) : 0;
-    if(m->graph1 && m->graph1_rows[0] == m->row0 && m->graph1_rows[1] == m->row1 && m->graph1_split == split)
+    const char* cforced = getenv("LCU_CONV_SMALL");
+    const int conv = cforced && *cforced ? (*cforced == '1') : -1;
+    if(m->graph1 && m->graph1_rows[0] == m->row0 && m->graph1_rows[1] == m->row1 && m->graph1_split == split
+       && m->graph1_conv == conv)
         return true;
     if(m->graph1)
     {
@@ -513,6 +524,7 @@ bool single_point_graph(lcu_model* m)
     m->graph1_rows[0] = m->row0;
     m->graph1_rows[1] = m->row1;
     m->graph1_split = split;
+    m->graph1_conv = conv;
     return true;
 }
 
@@ -949,7 +961,10 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_make_weight, m->mod, "lcu_make_weight")));
     if(m->has_psf)
+    {
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv, m->mod, "lcu_convolve")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_conv_small, m->mod, "lcu_convolve_small")));
+    }
 
     // constant tables: quadrature rule (src/lensed.c:817-823) and PSF (:808)
     {

@@ -516,6 +516,87 @@ lcu_convolve(const __grid_constant__ lcu_convolve_args a)
     }
 }
 
+// The same convolution for launches whose 64 x 32 tiles would leave most of the
+// machine idle (one point of a 100 x 100 image is 8 tiles on 148 SMs): a 32 x 8
+// tile per block, one pixel per thread, every tap read from shared memory.
+// Per pixel the products and sums are those of lcu_convolve in the same order,
+// and the chi^2 partial of a 32-pixel group is added up in the same shape
+// (eight consecutive pixels in sequence, then (s0 + s1) + (s2 + s3)), so both
+// kernels produce the same bits and the host picks by grid size alone.
+#define LCU_CS_W 32
+#define LCU_CS_H (LCU_BLOCK/32)
+#define LCU_CS_CW (LCU_CS_W + PSF_WIDTH - 1)
+#define LCU_CS_CH (LCU_CS_H + PSF_HEIGHT - 1)
+
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_convolve_small(const __grid_constant__ lcu_convolve_args a)
+{
+    __shared__ float tile[LCU_CS_CH][LCU_CS_CW];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int gx0 = blockIdx.x*LCU_CS_W;
+    const int gy0 = a.row0 + blockIdx.y*LCU_CS_H;
+
+    const float* raw = a.raw + (size_t)b*IMAGE_SIZE;
+
+    // edge-clamped window, kernel/lensed.cl:73-83
+    const int cx = gx0 - PSF_WIDTH/2;
+    const int cy = gy0 - PSF_HEIGHT/2;
+    for(int i = threadIdx.x; i < LCU_CS_CH*LCU_CS_CW; i += LCU_BLOCK)
+    {
+        const int r = i/LCU_CS_CW, c = i%LCU_CS_CW;
+        const int yy = min(max(cy + r, 0), IMAGE_HEIGHT - 1);
+        const int xx = min(max(cx + c, 0), IMAGE_WIDTH - 1);
+        tile[r][c] = raw[(size_t)yy*IMAGE_WIDTH + xx];
+    }
+    __syncthreads();
+
+    // PSF rows outer, columns inner (kernel/lensed.cl:95-97)
+    float acc = 0;
+#pragma unroll 1
+    for(int j = 0; j < PSF_HEIGHT; ++j)
+    {
+        const float* row = &tile[warp + PSF_HEIGHT - 1 - j][lane + PSF_WIDTH - 1];
+#pragma unroll
+        for(int i = 0; i < PSF_WIDTH; ++i)
+            acc = acc + lcu_psf[j*PSF_WIDTH + i]*row[-i];
+    }
+
+    const int gi = gx0 + lane;
+    const int gj = gy0 + warp;
+    const bool row_live = gj < a.row1;
+    double c = 0;
+    if(row_live && gi < IMAGE_WIDTH)
+    {
+        const size_t k = (size_t)gj*IMAGE_WIDTH + gi;
+        const size_t o = (size_t)b*IMAGE_SIZE + k;
+        if(a.mode & LCU_OUT_VALUE)
+            a.model[o] = acc;
+        // loglike kernel, kernel/lensed.cl:41-53
+        const float d = __fadd_rn(acc, -a.image[k]);
+        const float chi = __fmul_rn(__fmul_rn(a.weight[k], d), d);
+        if(a.mode & LCU_OUT_CHIMAP)
+            a.chimap[o] = chi;
+        c = (double)chi;
+    }
+    if(a.mode & LCU_OUT_CHI2)
+    {
+        // lcu_convolve's summation shape: a thread's 8 consecutive pixels one
+        // after the other, then the four threads of a group as (s0 + s1) + (s2 + s3)
+        double s = 0;
+#pragma unroll
+        for(int r = 0; r < 8; ++r)
+            s += __shfl_sync(0xffffffffu, c, (lane & 24) + r);
+        const double s01 = __shfl_sync(0xffffffffu, s, 0) + __shfl_sync(0xffffffffu, s, 8);
+        const double s23 = __shfl_sync(0xffffffffu, s, 16) + __shfl_sync(0xffffffffu, s, 24);
+        const int g = blockIdx.x;
+        if(lane == 0 && row_live && g < a.gpr)
+            a.partial[(size_t)b*a.ngroups + (size_t)(gj - a.row0)*a.gpr + g] = s01 + s23;
+    }
+}
+
 #endif // PSF
 
 // ---------------------------------------------------------------------------

@@ -153,9 +153,12 @@ def test_masked_pixels(gpu_ctx):
 
 
 @pytest.mark.parametrize("psf_shape", [(9, 9), (8, 8), (6, 11), (25, 25), (1, 1)])
-def test_convolution_shapes(gpu_ctx, psf_shape):
+@pytest.mark.parametrize("small", ["0", "1"])
+def test_convolution_shapes(gpu_ctx, psf_shape, small, monkeypatch):
     """Odd, even (half-pixel shift of src/lensed.c:885-891) and ragged PSFs; the
-    image is smaller than a tile in one direction so every edge clamp is hit."""
+    image is smaller than a tile in one direction so every edge clamp is hit.
+    Both convolution kernels: 64 x 32 tiles (small = 0) and 32 x 8 tiles."""
+    monkeypatch.setenv("LCU_CONV_SMALL", small)
     rng = np.random.default_rng(5)
     psf = H.workloads.normalise_psf(rng.random((psf_shape[1], psf_shape[0])) + 0.01)
     w = H.workloads.c4(64)
@@ -167,6 +170,35 @@ def test_convolution_shapes(gpu_ctx, psf_shape):
     # convolution alone is bit-exact given the same input (same summation order)
     conv = om.convolve(out["raw"])
     assert np.array_equal(out["model"].view(np.uint32), conv.view(np.uint32))
+
+
+@pytest.mark.parametrize("shape,psf_shape", [((100, 100), (9, 9)), ((45, 70), (13, 7)), ((33, 31), (4, 6)), ((120, 120), (21, 21))])
+def test_convolution_kernels_same_bits(gpu_ctx, monkeypatch, shape, psf_shape):
+    """The small-launch convolution (32 x 8 tiles, one pixel per thread) and the
+    register-tiled one give the same model image, chi^2 map and log-likelihood
+    to the last bit, for single points (graph path), batches and row strips."""
+    rng = np.random.default_rng(11)
+    psf = H.workloads.normalise_psf(rng.random((psf_shape[1], psf_shape[0])) + 0.01)
+    w = H.workloads.c4(max(shape))
+    img = rng.random(shape).astype(np.float32)
+    wht = (rng.random(shape) > 0.1).astype(np.float32)*rng.random(shape).astype(np.float32)
+    cfg = H.Config("conv2", w["objects"], w["truth"], img, wht, rule="sub2", psf=psf)
+    P = np.stack([cfg.params, cfg.params*np.float32(1.001), cfg.params*np.float32(0.999)])
+    res = {}
+    for small in ("0", "1"):
+        monkeypatch.setenv("LCU_CONV_SMALL", small)
+        m = cfg.product(gpu_ctx)
+        out = m.render(cfg.params)
+        one = [m.loglike(p) for p in P]
+        many = m.loglike_batch(P)
+        m.set_rows(5, shape[0] - 7)
+        strip = m.loglike_batch(P)
+        m.close()
+        res[small] = (out["model"], out["chi"], np.array(one), many, strip)
+    for a, b in zip(res["0"], res["1"]):
+        assert np.array_equal(a.view(np.uint64 if a.dtype == np.float64 else np.uint32),
+                              b.view(np.uint64 if b.dtype == np.float64 else np.uint32))
+    assert np.array_equal(res["0"][2], res["0"][3])
 
 
 def test_batch_and_split_invariance(gpu_ctx, monkeypatch):
