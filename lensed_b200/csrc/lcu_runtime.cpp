@@ -104,6 +104,13 @@ std::string library_dir()
 size_t div_up(size_t a, size_t b) { return (a + b - 1)/b; }
 
 // device-side argument blocks: must match kernel/lensed.cu
+struct Tail
+{
+    double* out;
+    unsigned* counter;
+    double scale;
+};
+
 struct RenderArgs
 {
     float pcs[4];
@@ -117,6 +124,7 @@ struct RenderArgs
     double* partial;
     int ngroups;
     int mode;
+    Tail tail;
 };
 
 struct ConvolveArgs
@@ -131,6 +139,7 @@ struct ConvolveArgs
     int ngroups;
     int gpr;
     int mode;
+    Tail tail;
 };
 
 enum { OUT_VALUE = 1, OUT_ERROR = 2, OUT_CHI2 = 4, OUT_CHIMAP = 8 };
@@ -168,6 +177,7 @@ struct lcu_model
     float* d_raw = nullptr;             // [raw_cap][size] rendered images, PSF models only; grows on demand
     size_t raw_cap = 0;
     double* d_partial = nullptr;        // [maxb][max groups]
+    unsigned* d_counter = nullptr;      // [maxb] finished blocks per point (fused reduction), zero between launches
     size_t partial_cap = 0;
     // staging for the host entry points
     float *d_params = nullptr, *h_params = nullptr;
@@ -179,6 +189,8 @@ struct lcu_model
     bool graph1_off = false;
     size_t graph1_rows[2] = { 0, 0 };
     int graph1_split = 0, graph1_conv = -1;
+    unsigned graph1_nodes = 0;          // kernel nodes of the graph
+    bool graph1_mapped = false;         // the graph writes its result straight into h_lnew
     // dumper buffers (one point), allocated on first lcu_render
     float *d_value1 = nullptr, *d_error1 = nullptr, *d_model1 = nullptr, *d_chi1 = nullptr;
     // profiling: one set of stage events per launched chunk, harvested lazily
@@ -303,10 +315,15 @@ int pick_split(const lcu_model* m, size_t npix, size_t nb)
 
 // enqueue set_params -> render -> (convolve) for `nb` points whose
 // parameters start at d_params; per-point outputs are optional
+// `reduce_out` (optional, with want_chi2): where scale * sum of each point's
+// chi^2 partials goes if the kernel that writes the partials can add them up
+// itself (the small-launch kernels); *reduced says whether it did
 int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t st,
                    float* value, float* error, float* model, float* chimap, bool want_chi2,
-                   cudaEvent_t* ev)
+                   cudaEvent_t* ev, double* reduce_out = nullptr, double scale = 1, bool* reduced = nullptr)
 {
+    if(reduced) *reduced = false;
+    const bool may_fuse = want_chi2 && reduce_out && reduced && !getenv("LCU_NO_FUSED_REDUCE");
     if(ev) cudaEventRecord(ev[0], st);
     // set_params, src/nested.c:77
     {
@@ -343,6 +360,12 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         a.partial = m->d_partial;
         a.ngroups = ngroups;
         a.mode = 0;
+        a.tail = Tail{ nullptr, nullptr, 0 };
+        if(may_fuse && !m->has_psf && split > 1)
+        {
+            a.tail = Tail{ reduce_out, m->d_counter, scale };
+            *reduced = true;
+        }
         if(a.value) a.mode |= OUT_VALUE;
         if(a.error) a.mode |= OUT_ERROR;
         if(!m->has_psf)
@@ -389,6 +412,12 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         const size_t big = div_up(m->width, 64)*div_up(rows, m->conv_tile_h)*nb;
         const char* force = getenv("LCU_CONV_SMALL");
         const bool small = force && *force ? *force == '1' : big < (size_t)std::max(m->ctx->sm_count, 1);
+        c.tail = Tail{ nullptr, nullptr, 0 };
+        if(may_fuse && small)
+        {
+            c.tail = Tail{ reduce_out, m->d_counter, scale };
+            *reduced = true;
+        }
         int rc = small
             ? launch(m, m->f_conv_small, dim3((unsigned)div_up(m->width, 32), (unsigned)div_up(rows, 8), (unsigned)nb), dim3(256), args, st)
             : launch(m, m->f_conv, dim3((unsigned)div_up(m->width, 64), (unsigned)div_up(rows, m->conv_tile_h), (unsigned)nb),
@@ -447,15 +476,21 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
     {
         const size_t nb = std::min(m->maxb, nbatch - b0);
         cudaEvent_t* ev = next_event_set(m, nb);
-        rc = enqueue_points(m, nb, d_params + b0*m->npars, st, nullptr, nullptr, nullptr, nullptr, true, ev);
-        if(rc) return rc;
-        // host sum of src/nested.c:106-115, on the device
-        int ng = ngroups;
+        // host sum of src/nested.c:106-115, on the device: by the last block of the
+        // kernel that writes the partials (small launches) or by a kernel of its own
         double scale = -0.5;
         double* out = d_lnew + b0;
-        void* args[] = { &ng, &m->d_partial, &scale, &out };
-        rc = launch(m, m->f_reduce, dim3((unsigned)nb), dim3(256), args, st);
+        bool reduced = false;
+        rc = enqueue_points(m, nb, d_params + b0*m->npars, st, nullptr, nullptr, nullptr, nullptr, true, ev,
+                            out, scale, &reduced);
         if(rc) return rc;
+        if(!reduced)
+        {
+            int ng = ngroups;
+            void* args[] = { &ng, &m->d_partial, &scale, &out };
+            rc = launch(m, m->f_reduce, dim3((unsigned)nb), dim3(256), args, st);
+            if(rc) return rc;
+        }
         if(ev) cudaEventRecord(ev[4], st);
     }
     return LCU_OK;
@@ -485,7 +520,9 @@ bool single_point_graph(lcu_model* m)
         return false;
     }
     cudaGraph_t graph = nullptr;
+    const unsigned long long launches0 = g_launches.load();
     bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    bool mapped = false;
     if(ok)
     {
         // The pinned staging buffers are mapped into the device's address space
@@ -495,7 +532,7 @@ bool single_point_graph(lcu_model* m)
         // restores them.
         float* dp = nullptr;
         double* dl = nullptr;
-        const bool mapped = !getenv("LCU_GRAPH_COPIES")
+        mapped = !getenv("LCU_GRAPH_COPIES")
             && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), m->h_params, 0) == cudaSuccess
             && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dl), m->h_lnew, 0) == cudaSuccess && dp && dl;
         if(!mapped)
@@ -510,6 +547,9 @@ bool single_point_graph(lcu_model* m)
         }
         ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
     }
+    // captured launches have not run: they count each time the graph is launched
+    m->graph1_nodes = (unsigned)(g_launches.load() - launches0);
+    g_launches.fetch_sub(m->graph1_nodes, std::memory_order_relaxed);
     if(ok)
         ok = cudaGraphInstantiate(&m->graph1, graph, 0) == cudaSuccess;
     if(graph)
@@ -525,6 +565,7 @@ bool single_point_graph(lcu_model* m)
     m->graph1_rows[1] = m->row1;
     m->graph1_split = split;
     m->graph1_conv = conv;
+    m->graph1_mapped = mapped;
     return true;
 }
 
@@ -540,7 +581,7 @@ void destroy_device_state(lcu_model* m)
         for(cudaEvent_t& e : es.e)
             cudaEventDestroy(e);
     m->evsets.clear();
-    void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_params, m->d_lnew,
+    void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_counter, m->d_params, m->d_lnew,
                      m->d_value1, m->d_error1, m->d_model1, m->d_chi1 };
     for(void* p : bufs)
         if(p) cudaFree(p);
@@ -997,6 +1038,8 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(RT_CHECK(cudaMemcpy(m->d_image, desc->image, m->size*sizeof(float), cudaMemcpyHostToDevice)));
     M_CHECK(RT_CHECK(cudaMemcpy(m->d_weight, desc->weight, m->size*sizeof(float), cudaMemcpyHostToDevice)));
     M_CHECK(RT_CHECK(cudaMalloc(&m->d_objs, m->maxb*m->words*sizeof(uint32_t))));
+    M_CHECK(RT_CHECK(cudaMalloc(&m->d_counter, m->maxb*sizeof(unsigned))));
+    M_CHECK(RT_CHECK(cudaMemset(m->d_counter, 0, m->maxb*sizeof(unsigned))));
     for(cudaEvent_t& e : m->ev_io)
         M_CHECK(RT_CHECK(cudaEventCreate(&e)));
     M_CHECK(return ensure_partial(m));
@@ -1177,9 +1220,28 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
     if(nbatch == 1 && !m->profile && single_point_graph(m))
     {
         memcpy(m->h_params, params, m->npars*sizeof(float));
+        // With mapped staging the last kernel stores the result in pinned host
+        // memory: watching that word is a few microseconds quicker than waiting for
+        // the runtime to report the stream idle.  The sentinel is a NaN pattern no
+        // arithmetic produces; the stream is queried now and then so that a failed
+        // launch ends the wait.
+        static const unsigned long long pending = 0x7ff8dead5eed0001ull;
+        volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(m->h_lnew);
+        const bool watch = m->graph1_mapped && !getenv("LCU_NO_POLL");
+        if(watch)
+            *word = pending;
         RT_CHECK(cudaGraphLaunch(m->graph1, m->stream));
-        g_launches.fetch_add(m->has_psf ? 4 : 3, std::memory_order_relaxed);
-        RT_CHECK(cudaStreamSynchronize(m->stream));
+        g_launches.fetch_add(m->graph1_nodes, std::memory_order_relaxed);
+        if(watch)
+        {
+            for(unsigned spins = 1; *word == pending; ++spins)
+                if((spins & 0xfff) == 0 && cudaStreamQuery(m->stream) != cudaErrorNotReady)
+                    break;
+            if(*word == pending)
+                RT_CHECK(cudaStreamSynchronize(m->stream));
+        }
+        else
+            RT_CHECK(cudaStreamSynchronize(m->stream));
         *lnew = m->h_lnew[0];
         return LCU_OK;
     }

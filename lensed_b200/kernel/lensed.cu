@@ -49,6 +49,16 @@ __constant__ float lcu_psf[PSF_WIDTH*PSF_HEIGHT];
 __constant__ uint4 lcu_objs_c[LCU_MAXB*LCU_WORDS/4];
 #endif
 
+// Final reduction fused into the kernel that writes the chi^2 partials (the
+// small-launch kernels only: one kernel node less on the single-point latency
+// path).  out == null: the host launches lcu_reduce instead.
+struct lcu_tail
+{
+    double* out;            // [B] scale * sum of the point's partials
+    unsigned* counter;      // [B] blocks of the point that have finished; zero between launches
+    double scale;
+};
+
 struct lcu_render_args
 {
     float4 pcs;             // (rx, ry, sx, sy), src/lensed.c:879-891
@@ -63,6 +73,7 @@ struct lcu_render_args
     double* partial;        // [B][ngroups]
     int ngroups;
     int mode;
+    lcu_tail tail;
 };
 
 // ---------------------------------------------------------------------------
@@ -86,6 +97,52 @@ lcu_set_params(int B, const float* __restrict__ params, uint* __restrict__ objs)
 #pragma unroll
     for(int i = 0; i < LCU_WORDS/4; ++i)
         out[i] = make_uint4(blk[4*i], blk[4*i+1], blk[4*i+2], blk[4*i+3]);
+}
+
+// ---------------------------------------------------------------------------
+// final reduction: one block per point, fixed summation shape
+// out = scale * sum_g partial[g]   (scale = -0.5 gives the log-likelihood
+// of src/nested.c:115; scale = 1 the chi^2 of one row strip)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lcu_reduce_block(int ngroups, const double* p, double scale, double* out)
+{
+    __shared__ double sm[LCU_BLOCK/32];
+
+    double s = 0;
+    for(int g = threadIdx.x; g < ngroups; g += LCU_BLOCK)
+        s += __ldcg(p + g);
+#pragma unroll
+    for(int off = 16; off > 0; off >>= 1)
+        s += __shfl_down_sync(0xffffffffu, s, off);
+    if((threadIdx.x & 31) == 0)
+        sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        double t = 0;
+#pragma unroll
+        for(int w = 0; w < LCU_BLOCK/32; ++w)
+            t += sm[w];
+        *out = scale*t;
+    }
+}
+
+// Called by every thread of every block of point b once the block's partials
+// are written: the block that finishes last adds them up, in lcu_reduce's shape.
+__device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsigned nblocks, int ngroups, const double* partial)
+{
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if(threadIdx.x == 0)
+        last = atomicAdd(t.counter + b, 1u) == nblocks - 1;
+    __syncthreads();
+    if(!last)
+        return;
+    __threadfence();
+    if(threadIdx.x == 0)
+        t.counter[b] = 0;
+    lcu_reduce_block(ngroups, partial + (size_t)b*ngroups, t.scale, t.out + b);
 }
 
 // ---------------------------------------------------------------------------
@@ -208,15 +265,15 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
             }
             __syncthreads();
         }
-        if(ns != 0)
-            return;
     }
+    // the warps that only helped with the quadrature points have no output
+    const bool writer = S == 1 || ns == 0;
 
     // outputs, kernel/lensed.cl:35-37, and the fused loglike kernel
     // (kernel/lensed.cl:41-53) when there is no PSF
     const size_t o = (size_t)b*IMAGE_SIZE + k;
     float chi = 0;
-    if(live)
+    if(live && writer)
     {
         if(a.mode & LCU_OUT_VALUE)
             a.value[o] = f0;
@@ -230,7 +287,7 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
                 a.chimap[o] = chi;
         }
     }
-    if(a.mode & LCU_OUT_CHI2)
+    if((a.mode & LCU_OUT_CHI2) && writer)
     {
         // fixed-shape tree over the 32 pixels of the group, in double
         double s = chi;
@@ -241,6 +298,9 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
         if(lane == 0 && g < a.ngroups)
             a.partial[(size_t)b*a.ngroups + g] = s;
     }
+    if constexpr(S > 1)
+        if(a.tail.out)
+            lcu_fused_reduce(a.tail, b, gridDim.x, a.ngroups, a.partial);
 }
 
 // Resident blocks per SM the compiler budgets registers for: 3 (<= 85
@@ -419,6 +479,7 @@ struct lcu_convolve_args
     int ngroups;
     int gpr;                // groups per row = ceil(IMAGE_WIDTH/32)
     int mode;
+    lcu_tail tail;
 };
 
 extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
@@ -595,6 +656,8 @@ lcu_convolve_small(const __grid_constant__ lcu_convolve_args a)
         if(lane == 0 && row_live && g < a.gpr)
             a.partial[(size_t)b*a.ngroups + (size_t)(gj - a.row0)*a.gpr + g] = s01 + s23;
     }
+    if(a.tail.out)
+        lcu_fused_reduce(a.tail, b, gridDim.x*gridDim.y, a.ngroups, a.partial);
 }
 
 #endif // PSF
@@ -617,33 +680,9 @@ lcu_make_weight(long long n, const float* __restrict__ image, const float* __res
     }
 }
 
-// ---------------------------------------------------------------------------
-// final reduction: one block per point, fixed summation shape
-// out[b] = scale * sum_g partial[b][g]   (scale = -0.5 gives the log-likelihood
-// of src/nested.c:115; scale = 1 the chi^2 of one row strip)
-// ---------------------------------------------------------------------------
+// the same reduction as a kernel of its own: one block per point
 extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
 lcu_reduce(int ngroups, const double* __restrict__ partial, double scale, double* __restrict__ out)
 {
-    __shared__ double sm[LCU_BLOCK/32];
-    const int b = blockIdx.x;
-    const double* p = partial + (size_t)b*ngroups;
-
-    double s = 0;
-    for(int g = threadIdx.x; g < ngroups; g += LCU_BLOCK)
-        s += p[g];
-#pragma unroll
-    for(int off = 16; off > 0; off >>= 1)
-        s += __shfl_down_sync(0xffffffffu, s, off);
-    if((threadIdx.x & 31) == 0)
-        sm[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        double t = 0;
-#pragma unroll
-        for(int w = 0; w < LCU_BLOCK/32; ++w)
-            t += sm[w];
-        out[b] = scale*t;
-    }
+    lcu_reduce_block(ngroups, partial + (size_t)blockIdx.x*ngroups, scale, out + blockIdx.x);
 }
