@@ -121,3 +121,81 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.abs(a - b)/np.maximum(np.abs(b), 1e-30)
+
+
+LENSES = ["sis", "sis_plus_shear", "sie", "sie_plus_shear", "nsis", "nsie", "epl", "epl_plus_shear", "point_mass"]
+SOURCES = ["sersic", "devauc", "exponential", "gauss", "sersic-old"]
+RULES = ["point", "sub2", "sub4", "gm75", "g3k7", "g5k11"]
+
+
+def _random_params(rng, name, width, height, role):
+    """Plausible parameters for one object from its metadata (kernel/object.cl
+    types): positions near the image centre, radii of a few pixels, and the
+    bounds the object declares for plain parameters."""
+    cx, cy = 0.5*(width + 1), 0.5*(height + 1)
+    vals = []
+    for p in O.object_info(name)["params"]:
+        t, pname = p["type"], p["name"]
+        if t == 1:
+            vals.append(cx + rng.uniform(-4, 4) + (rng.uniform(-6, 6) if role == "source" else 0))
+        elif t == 2:
+            vals.append(cy + rng.uniform(-4, 4) + (rng.uniform(-6, 6) if role == "source" else 0))
+        elif t == 3:
+            vals.append(rng.uniform(0.5, 2.0) if pname == "rc" else
+                        rng.uniform(0.15, 0.3)*min(width, height) if role == "lens" else rng.uniform(1.5, 6.0))
+        elif t == 4:
+            vals.append(rng.uniform(-5.0, -2.0))
+        elif t == 5:
+            vals.append(rng.uniform(0.4, 0.95))
+        elif t == 6:
+            vals.append(rng.uniform(0.0, 180.0))
+        elif pname in ("g1", "g2"):
+            vals.append(rng.uniform(-0.06, 0.06))
+        elif pname == "t":
+            vals.append(rng.uniform(0.7, 1.4))
+        elif pname == "n":
+            vals.append(rng.uniform(0.6, 5.0))
+        elif pname == "bg":
+            vals.append(rng.uniform(0.01, 0.1))
+        elif pname in ("dx", "dy"):
+            vals.append(rng.uniform(-3e-4, 3e-4))
+        else:
+            lo, hi = p["bounds"]
+            vals.append(rng.uniform(lo if np.isfinite(lo) else 0.1, hi if np.isfinite(hi) else 2.0))
+    return vals
+
+
+def random_config(seed: int) -> Config:
+    """A random model: optional unlensed host galaxy, one or two lenses in one
+    plane, one to three lensed sources, optional sky; random image shape,
+    quadrature rule and PSF (none / odd / even / ragged); observed image = the
+    strict-float32 oracle model plus seeded noise."""
+    rng = np.random.default_rng(1000 + seed)
+    height, width = int(rng.integers(36, 80)), int(rng.integers(36, 80))
+    objects, params = [], []
+
+    def add(name, role):
+        objects.append(name)
+        params.extend(_random_params(rng, name, width, height, role))
+    if rng.random() < 0.3:
+        add(str(rng.choice(SOURCES)), "host")
+    for _ in range(int(rng.integers(1, 3))):
+        add(str(rng.choice(LENSES)), "lens")
+    for _ in range(int(rng.integers(1, 4))):
+        add(str(rng.choice(SOURCES)), "source")
+    if rng.random() < 0.7:
+        add("sky", "sky")
+    kind = rng.integers(0, 4)
+    psf = None
+    if kind == 1:
+        psf = workloads.gaussian_psf(2*int(rng.integers(1, 5)) + 1, 2*int(rng.integers(1, 5)) + 1, rng.uniform(0.8, 2.0))
+    elif kind == 2:
+        psf = workloads.gaussian_psf(2*int(rng.integers(1, 4)), 2*int(rng.integers(1, 4)), rng.uniform(0.8, 2.0))
+    elif kind == 3:
+        psf = workloads.normalise_psf(rng.random((int(rng.integers(1, 9)), int(rng.integers(1, 9)))) + 0.05)
+    cfg = Config(name=f"random-{seed}", objects=objects, params=np.array(params, np.float32),
+                 image=np.zeros((height, width), np.float32), weight=np.ones((height, width), np.float32),
+                 rule=str(rng.choice(RULES)), psf=psf)
+    _, model, _ = cfg.oracle().loglike(cfg.params, want_maps=True)
+    cfg.image, cfg.weight = workloads.observe(model, 500 + seed, gain=200.0, offset=0.5)
+    return cfg

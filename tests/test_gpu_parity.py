@@ -67,16 +67,17 @@ def _check_images(out, cfg, om):
     return lnew, stats
 
 
-def _check_block(m, om, cfg):
+def _check_block(m, om, cfg, atol=1e-30):
     """Object data block written by set_params: same layout word for word;
     values agree to ~2 ulp (the setters evaluate their math built-ins in double
     on the device and round once; the host libm is not correctly rounded for
-    every function, e.g. tgammaf)."""
+    every function, e.g. tgammaf).  `atol`: for words that are a difference of
+    large terms (a Sersic log0 that happens to come out near zero)."""
     blk = m.set_params(cfg.params).view(np.float32)
     ref = om.set_params(cfg.params).astype(np.float32)
     assert blk.size == ref.size, f"{cfg.name}: object block size {blk.size} vs {ref.size}"
     assert np.array_equal(blk == 0, ref == 0), f"{cfg.name}: object block layout differs"
-    bad = ~np.isclose(blk, ref, rtol=5e-7, atol=1e-30)
+    bad = ~np.isclose(blk, ref, rtol=5e-7, atol=atol)
     assert not bad.any(), f"{cfg.name}: object block words {np.nonzero(bad)[0]}: {blk[bad]} vs {ref[bad]}"
 
 
@@ -444,6 +445,35 @@ def test_every_object_in_one_model(gpu_ctx, flags):
     got = m.loglike(params)
     assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew)          # 60^2 pixels
     _check_block(m, om, cfg)
+
+
+# seeds 0 ... 23 of helpers.random_config whose scene is well conditioned in
+# float32, screened on the CPU: the strict oracle is within 3.6e-6 of its
+# float64 twin at the 99.9th percentile (seeds 0, 1, 6, 7, 18, 22 are 5e-6 ...
+# 9e-6 from it, which leaves no room under the 1e-5 bound), and no pixel moves by
+# more than 1e-5 when sin / cos results change by one ulp (tools/libm_sensitivity.py;
+# seed 20 has one pixel on a critical curve of its epl_plus_shear lens that moves
+# by 1.6e-5 -- the CUDA path is 1.5e-5 from the oracle there, 1.5e-6 at p99.9)
+RANDOM_SEEDS = [2, 3, 4, 5, 8, 9, 11, 12, 13, 14, 15, 16, 17, 19, 21, 23]
+
+
+@pytest.mark.parametrize("flags", MATH_MODES)
+@pytest.mark.parametrize("seed", RANDOM_SEEDS)
+def test_random_models(gpu_ctx, seed, flags):
+    """Random combinations of the 15 objects (host galaxy, one or two lenses,
+    one to three sources, sky), random image shapes, quadrature rules and
+    PSFs: images, object block and log-likelihood against the oracle, and the
+    log-likelihood of a batch against the single-point path."""
+    cfg = H.random_config(seed)
+    om = cfg.oracle()
+    m = cfg.product(gpu_ctx, flags=flags)
+    out = m.render(cfg.params)
+    lnew, _ = _check_images(out, cfg, om)
+    got = m.loglike(cfg.params)
+    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew), f"{cfg.name} {cfg.objects}: lnew {got} vs {lnew}"
+    _check_block(m, om, cfg, atol=1e-6)
+    P = np.stack([cfg.params, cfg.params*np.float32(1.0005)])
+    assert np.array_equal(m.loglike_batch(P)[0], got)
 
 
 def test_pixel_coordinate_system(gpu_ctx):
