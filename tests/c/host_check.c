@@ -7,11 +7,14 @@
  *
  *   host_check meta                      object metadata + quadrature rules
  *   host_check loglike <device> <size>   a lens + source model on a blank image
+ *   host_check latency <device> <size> <n>   n one-point calls in a row, as MultiNest would make them
  */
+#define _POSIX_C_SOURCE 199309L
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "lensed_cuda.h"
 
@@ -130,12 +133,64 @@ static int loglike(int device, size_t size)
     return 0;
 }
 
+/* the sampler's callback pattern (src/nested.c:63-115): one point per call, the
+   next call needs the previous result; prints the mean time per call */
+static int latency(int device, size_t size, int n)
+{
+    lcu_ctx* ctx;
+    lcu_model* model;
+    CHECK(lcu_create(device, NULL, NULL, &ctx));
+    lcu_object_spec objs[2] = { { "sie", NULL }, { "sersic", NULL } };
+    int nq = lcu_quad_rule("g3k7", 1, 1, NULL, NULL);
+    float* qq = malloc(2*nq*sizeof(float));
+    float* ww = malloc(2*nq*sizeof(float));
+    lcu_quad_rule("g3k7", 1, 1, qq, ww);
+    float* image = calloc(size*size, sizeof(float));
+    float* weight = malloc(size*size*sizeof(float));
+    for(size_t i = 0; i < size*size; ++i)
+        weight[i] = 1.0f;
+    float psf[81];
+    for(int i = 0; i < 81; ++i)
+        psf[i] = 1.0f/81;
+    lcu_model_desc desc;
+    memset(&desc, 0, sizeof(desc));
+    desc.width = desc.height = size;
+    desc.pcs[0] = desc.pcs[1] = desc.pcs[2] = desc.pcs[3] = 1;
+    desc.nq = (size_t)nq; desc.qq = qq; desc.ww = ww;
+    desc.image = image; desc.weight = weight;
+    desc.psf = psf; desc.psf_width = desc.psf_height = 9;
+    desc.flags = LCU_FAST_INTRINSICS | LCU_FAST_ATANH;
+    CHECK(lcu_model_create(ctx, objs, 2, &desc, &model));
+    const float c = 0.5f*(float)(size + 1);
+    float p[12] = { c, c, 0.2f*(float)size, 0.75f, 45.f, c + 2.f, c + 1.f, 0.04f*(float)size, -3.f, 2.f, 0.8f, 30.f };
+    double lnew = 0, sum = 0;
+    for(int i = 0; i < 20; ++i)
+        CHECK(lcu_loglike(model, p, &lnew));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for(int i = 0; i < n; ++i)
+    {
+        p[3] = 0.75f + 1e-4f*(float)(i & 15);
+        CHECK(lcu_loglike(model, p, &lnew));
+        sum += lnew;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double us = ((double)(t1.tv_sec - t0.tv_sec)*1e9 + (double)(t1.tv_nsec - t0.tv_nsec))/1e3/n;
+    printf("latency %.3f us per lcu_loglike (%d calls, %zux%zu, sie + sersic, 9x9 PSF, g3k7) checksum %.9g\n", us, n, size, size, sum);
+    lcu_model_destroy(model);
+    lcu_destroy(ctx);
+    free(qq); free(ww); free(image); free(weight);
+    return 0;
+}
+
 int main(int argc, char* argv[])
 {
     if(argc >= 2 && strcmp(argv[1], "meta") == 0)
         return meta();
     if(argc >= 4 && strcmp(argv[1], "loglike") == 0)
         return loglike(atoi(argv[2]), (size_t)atol(argv[3]));
-    fprintf(stderr, "usage: host_check meta | loglike <device> <size>\n");
+    if(argc >= 5 && strcmp(argv[1], "latency") == 0)
+        return latency(atoi(argv[2]), (size_t)atol(argv[3]), atoi(argv[4]));
+    fprintf(stderr, "usage: host_check meta | loglike <device> <size> | latency <device> <size> <n>\n");
     return 2;
 }

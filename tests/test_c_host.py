@@ -65,3 +65,15 @@ def test_loglike_from_c(host_check):
     assert np.float32(float(prep[2])) == np.float32(np.float32(1800.0)/np.float64(2.9633)) and float(prep[3]) == 0.0
     assert float(prep[4]) != lnew[0]
     assert out[4].split()[0] == "back" and float(out[4].split()[1]) == lnew[0]          # original weights restored
+
+
+@pytest.mark.gpu
+def test_single_point_latency_from_c(host_check):
+    """The sampler's callback pattern from a C host: one point per call on a
+    100 x 100 image (the reference's example size).  The reference's CPU build
+    takes ~2 ms per call on 16 threads; anything above 200 us here means the
+    graph path is not in use."""
+    out = subprocess.run([host_check, "latency", "0", "100", "2000"], check=True, capture_output=True, text=True).stdout
+    print(out)
+    us = float(out.split()[1])
+    assert 0 < us < 200
