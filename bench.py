@@ -319,7 +319,11 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "lcu_render_pair" if model.rays_per_thread == 2 else "lcu_render_s1", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved/fp32_peak if achieved and fp32_peak else None, "traffic": traffic,
+                "frac": achieved/fp32_peak if achieved and fp32_peak else None,
+                # the reference's arithmetic is FMUL + FADD where an FMA would do (no contraction, parity):
+                # source-level flops can reach at most half the FFMA peak
+                "frac_of_unfused_ceiling": achieved/(0.5*fp32_peak) if achieved and fp32_peak else None,
+                "traffic": traffic,
                 "peak_source": "FFMA micro-benchmark run in this process (MEASURED_PEAKS.json records no FP32 peak)",
                 "algorithmic": f"{w['flops_per_ray']} flop + {w['transc_per_ray']} transcendental calls per ray x "
                                f"{work['rays']} rays x {B} points per launch",
