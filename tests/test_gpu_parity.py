@@ -610,6 +610,29 @@ def test_two_rays_per_thread_underflow(gpu_ctx, monkeypatch, flags):
         assert np.all(np.abs(a[~normal].astype(np.float64) - b[~normal]) <= tiny), objects
 
 
+@pytest.mark.parametrize("flags", MATH_MODES)
+def test_exponential_overflow_is_infinite(gpu_ctx, flags):
+    """exp of an argument above 88.7 is +inf, never NaN, in both math modes and
+    in both render kernels (the compensated hardware exp multiplies 2^t = inf by
+    a correction factor, which must not be negative there): an absurdly bright
+    Sersic source overflows in the pixels around its centre and is an ordinary
+    profile further out."""
+    import lensed_b200 as L
+    img = np.zeros((48, 48), np.float32)
+    params = np.array([24.4, 24.7, 3.0, -103.0, 1.0, 0.8, 30.0], np.float32)
+    cfg = H.Config("overflow", ["sersic"], params, img, np.ones_like(img), rule="sub4")
+    ref, _ = cfg.oracle().render(params)
+    r64, _ = cfg.oracle(variant="f64").render(params)
+    fmax = float(np.finfo(np.float32).max)
+    over, under = r64 > 10*fmax, r64 < 0.1*fmax      # pixels on the threshold may go either way
+    assert over.sum() >= 8 and under.sum() > 1000 and np.isinf(ref[over]).all() and not np.isnan(ref).any()
+    for extra in (0, L.LCU_NO_PAIR):
+        got = cfg.product(gpu_ctx, flags=flags | extra).render(params)["raw"]
+        assert not np.isnan(got).any()
+        assert np.isinf(got[over]).all() and (got[over] > 0).all()
+        assert H.rel_err(got[under], ref[under]).max() <= PIXEL_TOL
+
+
 def test_fma_contraction_flag(gpu_ctx, monkeypatch):
     """LCU_FAST_MATH (FMA contraction, what -cl-fast-relaxed-math allows the
     reference's compiler) is opt-in: it stays close to the strict result but
