@@ -183,6 +183,11 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
     s << "//----------------------------------------------------------------------------\n"
       << "// objects/" << name << ".cl\n"
       << "//----------------------------------------------------------------------------\n"
+      // every copy of the plugin text lives in a namespace of its own (lcu_ray,
+      // lcu_setter, lcu_pair): a helper function the plugin defines exists once
+      // per copy, and argument-dependent lookup (the vector types are global)
+      // must not find the other copies' versions
+      << "namespace lcu_ray {\n"
       << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
       << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"
       << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_ON\n#include \"shim.cuh\"\n#endif\n"
@@ -204,7 +209,8 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "    (unsigned int)type_" << id << ",\n"
       << "    (unsigned int)sizeof(struct data_" << id << "),\n"
       << "    (unsigned int)(sizeof(lcu_parlst_" << id << ")/sizeof(struct param))\n"
-      << "};\n\n";
+      << "};\n"
+      << "} // namespace lcu_ray\n\n";
     // Second copy of the object for the parameter setter (and the ray shots
     // of image-plane priors): same text, but its math built-ins are evaluated
     // in double and rounded once (shim.cuh: LCU_ACCURATE_ON).  set_params runs
@@ -236,7 +242,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
       << "#define LCU_PAIR_ON\n#include \"shim.cuh\"\n"
       << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"
       << "#if LCU_ATANH_@KIND@\n#define LCU_ATANH_ON\n#include \"shim.cuh\"\n#endif\n"
-      << "#define data struct ::data_" << id << "\n"
+      << "#define data struct ::lcu_ray::data_" << id << "\n"
       << "#define deflection deflection_" << id << "\n"
       << "#define brightness brightness_" << id << "\n"
       << "#define foreground foreground_" << id << "\n"
@@ -267,7 +273,7 @@ std::string generate_compute(const std::vector<ModelObject>& objs, bool pair)
     // pair: the same function for two rays per thread, on the lcu_pair copies
     // of the objects (lcu_compute2, shim.cuh: packed pairs)
     const char* V2 = pair ? "lcu_pf2" : "lcu_float2";
-    const char* NS = pair ? "lcu_pair::" : "";
+    const char* NS = pair ? "lcu_pair::" : "lcu_ray::";
     const std::string DEFLECT = pair ? " -= lcu_pair_guard(a);\n" : lcu::DEFLECT;
     std::ostringstream s;
     s << "__device__ __forceinline__ " << (pair ? "lcu_pf lcu_compute2" : "float lcu_compute") << "(const uint* data, " << V2 << " x)\n{\n"
@@ -306,13 +312,13 @@ std::string generate_compute(const std::vector<ModelObject>& objs, bool pair)
         const char* ind = open ? "        " : "    ";
         if(t == LCU_LENS)
         {
-            s << ind << (first_lens ? "a = " : "a += ") << NS << "deflection_" << id << "((struct data_" << id << "*)(data + " << o.d << "), y);\n";
+            s << ind << (first_lens ? "a = " : "a += ") << NS << "deflection_" << id << "((struct lcu_ray::data_" << id << "*)(data + " << o.d << "), y);\n";
             first_lens = false;
         }
         else
         {
             s << ind << (first_light ? "f = " : "f += ") << NS << (t == LCU_SOURCE ? "brightness_" : "foreground_") << id
-              << "((struct data_" << id << "*)(data + " << o.d << "), " << (t == LCU_SOURCE ? "y" : "x") << ");\n";
+              << "((struct lcu_ray::data_" << id << "*)(data + " << o.d << "), " << (t == LCU_SOURCE ? "y" : "x") << ");\n";
             first_light = false;
         }
     }

@@ -21,11 +21,11 @@ def test_compute_order_host_lens_source_sky(compile_ctx):
     body = _body(m.source, "float lcu_compute(")
     lines = [l.strip() for l in body.splitlines() if "+=" in l or "-=" in l]
     lines = [l.strip() for l in body.splitlines() if " = " in l and ("deflection_" in l or "brightness_" in l or "foreground_" in l) or "+=" in l or "-=" in l]
-    assert lines[0].startswith("f = brightness_sersic((struct data_sersic*)(data + 0), y)")        # unlensed host
-    assert lines[1].startswith("a = deflection_sie((struct data_sie*)(data + 12), y)")
+    assert lines[0].startswith("f = lcu_ray::brightness_sersic((struct lcu_ray::data_sersic*)(data + 0), y)")        # unlensed host
+    assert lines[1].startswith("a = lcu_ray::deflection_sie((struct lcu_ray::data_sie*)(data + 12), y)")
     assert lines[2].startswith("y -= dot(a, a) < HUGE_VALF ? a : lcu_float2(1E10f, 1E10f)")        # non-finite guard
-    assert lines[3].startswith("f += brightness_sersic((struct data_sersic*)(data + 28), y)")      # lensed source
-    assert lines[4].startswith("f += foreground_sky((struct data_sky*)(data + 40), x)")            # image plane
+    assert lines[3].startswith("f += lcu_ray::brightness_sersic((struct lcu_ray::data_sersic*)(data + 28), y)")      # lensed source
+    assert lines[4].startswith("f += lcu_ray::foreground_sky((struct lcu_ray::data_sky*)(data + 40), x)")            # image plane
     assert m.words == 44 and m.npars == 7 + 5 + 7 + 3
 
 
@@ -69,7 +69,7 @@ def test_pair_copy_of_every_shipped_object(compile_ctx):
     m = L.Model(compile_ctx, ["sie_plus_shear", "sersic", "sky"], IMG, IMG)
     assert m.rays_per_thread == 2
     assert "lcu_pf lcu_compute2(const uint* data, lcu_pf2 x)" in m.source
-    assert "a = lcu_pair::deflection_sie_plus_shear((struct data_sie_plus_shear*)(data + 0), y);" in m.source
+    assert "a = lcu_pair::deflection_sie_plus_shear((struct lcu_ray::data_sie_plus_shear*)(data + 0), y);" in m.source
     assert "y -= lcu_pair_guard(a);" in m.source
     m1 = L.Model(compile_ctx, ["sie_plus_shear", "sersic", "sky"], IMG, IMG, flags=L.LCU_NO_PAIR)
     assert m1.rays_per_thread == 1 and "lcu_pf lcu_compute2(" not in m1.source
@@ -140,3 +140,112 @@ def test_render_kernels_keep_the_object_block_out_of_vector_registers(compile_ct
     assert regs <= 85 and stack <= 64, (regs, stack)
     with pytest.raises(L.LensedCudaError):
         m.kernel_usage("no_such_kernel")
+
+
+TRICKY = r'''// a plugin written to trip a text-based loader: } { ; set( in comments and strings of macros
+/* type = LENS;   params { {"nope"} };   static void set(local data* this) { } */
+#define TWICE(v) ((v) + (v))   /* macros of the plugin's own: } */
+#define AMPLITUDE(self) ((self)->amp)
+
+type = SOURCE;
+
+params {
+    { "x", POSITION_X },   // comment with a brace }
+    { "y", POSITION_Y },
+    { "width", RADIUS, { 0.5f, 100.f }, 2.0f },
+    { "amp", PARAMETER, POS_BOUND }
+};
+
+data
+{
+    float2 centre;   /* }; */
+    float inv_w;
+    float amp;
+};
+
+// helper functions before and after the entry points, with the OpenCL qualifiers the docs use
+static float bump(float u)
+{
+    return exp(-0.5f*u);
+}
+
+static float brightness(constant data* this, float2 x)
+{
+    float2 d = (x - this->centre)*this->inv_w;
+    float2 e = (float2)(TWICE(d.x), (float2)(d.y, 0.0f).x);
+    return AMPLITUDE(this)*bump(0.25f*dot(e, e) + d.y*d.y*0.0f);
+}
+
+static float unused_helper(global data* this)
+{
+    return this->amp;   // set(this, 1, 2, 3, 4);
+}
+
+static void set(local data* this, float x, float y, float width, float amp)
+{
+    this->centre = (float2)(x, y);
+    if(width > 0)       // branches on parameters are fine in set()
+        this->inv_w = 1/width;
+    else
+        this->inv_w = 0;
+    this->amp = amp;
+}
+'''
+
+
+SWIZZLE = r'''type = LENS;
+params { {"x", POSITION_X}, {"y", POSITION_Y}, {"r", RADIUS}, {"pa", POS_ANGLE} };
+data { float2 c; mat22 m; float r; };
+// a helper with vector arguments: every copy of the plugin text has its own,
+// and argument-dependent lookup must not mix them up
+static float2 rot(mat22 m, float2 v) { return (float2)(dot(m.lo, v), dot(m.hi, v)); }
+static float2 deflection(local data* this, float2 x)
+{
+    float2 d = rot(this->m, x - this->c);
+    float n = length(d);
+    float2 u = normalize(d);
+    float4 w = (float4)(u, d.s0, d.s1);          // mixed vector literal
+    float4 z = (float4)(0.0f, u, 1.0f) + (float4)(n, n, w.zw);
+    return this->r*(float2)(w.x + 0*z.z, w.s1 + 0*z.w)*fmin(n, 1.0f);
+}
+static void set(local data* this, float x, float y, float r, float pa)
+{
+    float c;
+    float s = sincos(pa*DEG2RAD, &c);
+    this->c = (float2)(x, y);
+    this->m = (mat22)(c, s, -s, c);
+    this->r = r;
+}
+'''
+
+
+def test_plugin_text_with_comments_macros_helpers_and_qualifiers(tmp_path):
+    """The loader works on text (name mangling by macros as src/kernel.c:153-172,
+    vector literals rewritten, type / params / data / set() blanked out of the
+    pair copy): braces and keywords in comments, the plugin's own macros, helper
+    functions, nested vector literals and all three address-space qualifiers of
+    docs/create.md must survive it -- in the scalar, the setter and the pair copy."""
+    import shutil
+    objdir = tmp_path / "objects"
+    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    (objdir / "tricky.cl").write_text(TRICKY)
+    ctx = L.Context(device=-1, objects_dir=str(objdir))
+    try:
+        info = ctx.object_info("tricky")
+        assert info.type == "S" and info.words == 4
+        assert [p.name for p in info.params] == ["x", "y", "width", "amp"]
+        assert info.params[2].bounds == (0.5, 100.0) and info.params[2].defval == 2.0
+        assert info.params[3].bounds[0] == 0.0 and info.params[3].bounds[1] > 1e30
+        ok, why = ctx.object_pairable("tricky")
+        assert ok, why
+        m = L.Model(ctx, ["sie", "tricky", "tricky", "sky"], IMG, IMG)
+        assert m.rays_per_thread == 2 and m.npars == 5 + 4 + 4 + 3
+        assert len(m.cubin) > 0
+        # vector-typed helper, .lo/.hi/.s0/.zw swizzles, mixed vector literals; also as the
+        # lens an image-plane prior is shot through (the setter copy calls its own helper)
+        (objdir / "swizzle.cl").write_text(SWIZZLE)
+        assert ctx.object_info("swizzle").words == 12 and ctx.object_pairable("swizzle")[0]
+        m = L.Model(ctx, ["swizzle", "sie", "tricky"], IMG, IMG, ipp=[[0]*4, [0]*5, [1, 1, 0, 0]])
+        assert m.rays_per_thread == 2 and "lcu_setter::deflection_swizzle" in _body(m.source, "void lcu_set_params_body")
+    finally:
+        ctx.close()
