@@ -77,10 +77,11 @@ std::string make_ident(const std::string& name)
 
 // The pair copy of an object (two rays per thread, shim.cuh) needs only the
 // functions that run per ray.  Everything that describes or fills the data
-// block -- `type = ...;`, `params {...};`, `data {...};` and the set() function
-// -- is blanked out of that copy (newlines kept, so that diagnostics still
-// point at the right line): the data block has one layout, defined by the
-// scalar copy, and set() may branch on its arguments, which pairs cannot.
+// block -- `type = ...;`, `params {...};`, `data {...};`, the set() function --
+// and program-scope constants are blanked out of that copy (newlines kept, so
+// that diagnostics still point at the right line): the data block has one
+// layout, defined by the scalar copy, set() may branch on its arguments, which
+// pairs cannot, and a constant is the same number for both rays.
 // A small scanner rather than a parser: top-level items end at a ';' or at the
 // '}' that closes a function body; comments, literals and preprocessor lines
 // are skipped over.
@@ -98,12 +99,14 @@ std::string strip_for_pair(const std::string& text)
         // identifiers outside comments up to the first '{' or '='
         std::vector<std::string> ids;
         bool call_set = false;
+        bool variable = false;      // "<qualifiers> <type> name[...] = ...;": a program-scope constant
         for(size_t i = item; i < end; )
         {
             const char c = text[i];
             if(c == '/' && i + 1 < end && text[i + 1] == '/') { while(i < end && text[i] != '\n') ++i; continue; }
             if(c == '/' && i + 1 < end && text[i + 1] == '*') { i += 2; while(i + 1 < end && !(text[i] == '*' && text[i + 1] == '/')) ++i; i += 2; continue; }
-            if(c == '{' || c == '=') break;
+            if(c == '=') { variable = true; break; }
+            if(c == '{') break;
             if(is_id(c))
             {
                 size_t j = i;
@@ -120,7 +123,9 @@ std::string strip_for_pair(const std::string& text)
             if(c == '(') { break; }
             ++i;
         }
-        const bool drop = call_set || (!ids.empty() && (ids[0] == "type" || ids[0] == "params" || ids[0] == "data"));
+        // program-scope constants stay what the scalar copy made of them (plain floats,
+        // visible here through the using-directive of the pair namespace)
+        const bool drop = call_set || variable || (!ids.empty() && (ids[0] == "type" || ids[0] == "params" || ids[0] == "data"));
         if(drop)
             for(size_t i = item; i < end; ++i)
                 if(out[i] != '\n')
@@ -237,7 +242,7 @@ std::string wrap_object(const std::string& name, const std::string& id, const st
     // functions with float = a packed pair (shim.cuh), the data block shared
     // with the scalar copy.  Only compiled when every object of the model
     // can be typed that way (LCU_PAIR, decided in lcu_ctx::object).
-    s << "#if LCU_PAIR\nnamespace lcu_pair {\n"
+    s << "#if LCU_PAIR\nnamespace lcu_pair {\nusing namespace ::lcu_ray;\n"
       << "#define LCU_SHIM_ON\n#include \"shim.cuh\"\n"
       << "#define LCU_PAIR_ON\n#include \"shim.cuh\"\n"
       << "#if LCU_INTRINSICS_@KIND@\n#define LCU_INTRINSICS_ON\n#include \"shim.cuh\"\n#endif\n"

@@ -249,3 +249,73 @@ def test_plugin_text_with_comments_macros_helpers_and_qualifiers(tmp_path):
         assert m.rays_per_thread == 2 and "lcu_setter::deflection_swizzle" in _body(m.source, "void lcu_set_params_body")
     finally:
         ctx.close()
+
+
+BUILTINS = r'''type = SOURCE;
+params { {"x", POSITION_X}, {"y", POSITION_Y}, {"r", RADIUS}, {"a"} };
+data { float2 c; float r; float a; float4 k; };
+
+__constant float COEFF[4] = { 1.0f, 0.5f, 0.25f, 0.125f };
+constant float SCALE = 2.0f;
+
+static float poly(float u)
+{
+    float s = 0;
+    for(int i = 0; i < 4; ++i)
+        s = s*u + COEFF[i];
+    return s;
+}
+
+static float brightness(__local data* this, float2 x)
+{
+    float2 d = (x - this->c)/this->r;
+    float q = clamp(hypot(d.x, d.y), 0.0f, 10.0f);
+    float t = fmax(fmin(q, 4.0f), 0.1f) + fabs(d.x)*0 + sign(d.y)*0 + step(0.5f, q)*0 + smoothstep(0.0f, 1.0f, q)*0;
+    t += exp2(-q) + log1p(q)*0 + expm1(q)*0 + native_exp(-q)*0 + half_exp(-q)*0 + native_sqrt(q)*0 + rsqrt(q + 1.0f)*0;
+    t += mix(0.0f, 1.0f, 0.5f)*0 + mad(q, 0.0f, 0.0f) + pown(q, 2)*0 + powr(q + 1, 0.5f)*0 + pow(q + 1, 2.0f)*0;
+    t += degrees(0.0f) + radians(0.0f) + M_PI_F*0 + FLT_MAX*0 + FLT_EPSILON*0;
+    t += (isnan(q) ? 1.0f : 0.0f)*0 + (isfinite(q) ? 0.0f : 1.0f) + (float)(isinf(q))*0;
+    t += dot(this->k, this->k)*0 + length(this->k.xy)*0 + distance(d, d) + fast_length(d)*0;
+    t += atan2(d.y, d.x)*0 + sinh(q)*0 + cosh(q)*0 + tanh(q)*0 + asin(0.5f)*0 + acos(0.5f)*0 + cbrt(q)*0 + erf(q)*0 + erfc(q)*0;
+    t += floor(q)*0 + ceil(q)*0 + round(q)*0 + trunc(q)*0 + fmod(q, 2.0f)*0 + copysign(q, -1.0f)*0 + fdim(q, 1.0f)*0;
+    return this->a*SCALE*poly(t);
+}
+
+static void set(__local data* this, float x, float y, float r, float a)
+{
+    this->c = (float2)(x, y);
+    this->r = r;
+    this->a = a*tgamma(2.0f)/exp(lgamma(2.0f));
+    this->k = (float4)(1.0f);
+    this->k.lo = (float2)(x, y);
+    this->k.s3 = as_float(as_int(r));
+    uint n = (uint)convert_int(r);
+    this->k.z = (float)n + convert_float(3);
+}
+'''
+
+
+def test_opencl_builtins_a_plugin_may_call(tmp_path):
+    """OpenCL C built-ins beyond what the shipped objects use (common, math,
+    geometric, reinterpretation and conversion functions, __-prefixed address
+    spaces, program-scope constant arrays) compile in the scalar and the setter
+    copy; the pair copy takes everything except the classification functions
+    on ray values (isnan / isinf / isfinite: a per-ray decision), with which
+    the model falls back to one ray per thread."""
+    import shutil
+    objdir = tmp_path / "objects"
+    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    (objdir / "builtins.cl").write_text(BUILTINS)
+    (objdir / "builtins2.cl").write_text("\n".join(l for l in BUILTINS.splitlines() if "isnan(" not in l))
+    ctx = L.Context(device=-1, objects_dir=str(objdir))
+    try:
+        assert ctx.object_info("builtins").words == 8
+        ok, why = ctx.object_pairable("builtins")
+        errors = [l for l in why.splitlines() if "error:" in l]
+        assert not ok and len(errors) == 3 and all(("isnan" in e) or ("isinf" in e) or ("isfinite" in e) for e in errors), why
+        assert L.Model(ctx, ["sie", "builtins"], IMG, IMG).rays_per_thread == 1
+        ok, why = ctx.object_pairable("builtins2")
+        assert ok, why
+        assert L.Model(ctx, ["sie", "builtins2"], IMG, IMG).rays_per_thread == 2
+    finally:
+        ctx.close()
