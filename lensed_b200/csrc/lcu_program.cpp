@@ -52,7 +52,11 @@ std::string read_text_file(const std::string& path, bool* ok)
     std::ostringstream ss;
     ss << f.rdbuf();
     *ok = true;
-    return ss.str();
+    std::string text = ss.str();
+    // a UTF-8 byte order mark some editors put first is not part of the program
+    if(text.size() >= 3 && (unsigned char)text[0] == 0xEF && (unsigned char)text[1] == 0xBB && (unsigned char)text[2] == 0xBF)
+        text.erase(0, 3);
+    return text;
 }
 
 // OpenCL vector literals "(float2)(a, b)" are a cast applied to a comma

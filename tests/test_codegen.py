@@ -319,3 +319,33 @@ def test_opencl_builtins_a_plugin_may_call(tmp_path):
         assert L.Model(ctx, ["sie", "builtins2"], IMG, IMG).rays_per_thread == 2
     finally:
         ctx.close()
+
+
+def test_object_file_encodings_and_function_specifiers(tmp_path):
+    """Windows line ends, a UTF-8 byte order mark, a missing final newline;
+    `static inline`, plain `inline` and non-static helper functions; the
+    stray ';' after function bodies that docs/create.md:113,149 has."""
+    import shutil
+    objdir = tmp_path / "objects"
+    src = os.path.join(os.path.dirname(L.__file__), "objects")
+    shutil.copytree(src, objdir)
+    sersic = open(os.path.join(src, "sersic.cl")).read()
+    sie = open(os.path.join(src, "sie.cl")).read()
+    (objdir / "crlf.cl").write_bytes(sersic.replace("\n", "\r\n").encode())
+    (objdir / "bom.cl").write_bytes(b"\xef\xbb\xbf" + sersic.encode())
+    (objdir / "nonl.cl").write_bytes(sersic.rstrip("\n").encode())
+    helpers = sie.replace("static float2 deflection", "float sq(float v) { return v*v; }\ninline float tw(float v) { return v + v; }\n"
+                          "static inline float2 deflection").replace("v.y*v.y", "sq(v.y) + 0*tw(v.x)")
+    assert helpers != sie
+    (objdir / "helpers.cl").write_text(helpers.replace("\n}\n", "\n};\n"))
+    ctx = L.Context(device=-1, objects_dir=str(objdir))
+    try:
+        ref = ctx.object_info("sersic")
+        for name in ("crlf", "bom", "nonl"):
+            info = ctx.object_info(name)
+            assert (info.type, info.words, [p.name for p in info.params]) == (ref.type, ref.words, [p.name for p in ref.params])
+            assert ctx.object_pairable(name)[0]
+        assert ctx.object_info("helpers").words == ctx.object_info("sie").words and ctx.object_pairable("helpers")[0]
+        assert L.Model(ctx, ["helpers", "crlf", "bom", "nonl"], IMG, IMG).rays_per_thread == 2
+    finally:
+        ctx.close()
