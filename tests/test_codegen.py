@@ -349,3 +349,47 @@ def test_object_file_encodings_and_function_specifiers(tmp_path):
         assert L.Model(ctx, ["helpers", "crlf", "bom", "nonl"], IMG, IMG).rays_per_thread == 2
     finally:
         ctx.close()
+
+
+VECTOR_BUILTINS = r'''type = LENS;
+params { {"x", POSITION_X}, {"y", POSITION_Y}, {"r", RADIUS} };
+data { float2 c; float r; };
+static float2 deflection(local data* this, float2 x)
+{
+    float2 d = x - this->c;
+    float2 a = fabs(d);
+    float2 b = sqrt(a*a + 1.0f);
+    float2 e = exp(-a)*0.0f + log(b)*0.0f + sin(d)*0.0f + cos(d)*0.0f;
+    float2 f = fmax(a, 0.5f) + fmin(a, (float2)(2.0f, 3.0f))*0.0f + clamp(d, -1.0f, 1.0f)*0.0f + mix(a, b, 0.5f)*0.0f;
+    float2 g = pow(b, 2.0f)*0.0f + atan2(d, b)*0.0f + sign(d)*0.0f + floor(d)*0.0f;
+    return this->r*d/(f + e + g);
+}
+static void set(local data* this, float x, float y, float r)
+{
+    this->c = (float2)(x, y);
+    this->r = r;
+}
+'''
+
+
+def test_gentype_builtins_on_vectors(tmp_path):
+    """OpenCL math and common functions take vectors (gentype): exp(float2),
+    fmax(float2, float), clamp(float2, float, float), ... -- component by
+    component, in every copy of the text and under every math mode (the modes
+    substitute function names, so each substituted name needs the vector forms
+    too), also in the lens an image-plane prior is shot through."""
+    import shutil
+    objdir = tmp_path / "objects"
+    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    (objdir / "vecfn.cl").write_text(VECTOR_BUILTINS)
+    ctx = L.Context(device=-1, objects_dir=str(objdir))
+    try:
+        assert ctx.object_info("vecfn").words == 4
+        ok, why = ctx.object_pairable("vecfn")
+        assert ok, why
+        for flags in (0, L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH, L.LCU_FAST_INTRINSICS | L.LCU_FAST_LENS_INTRINSICS | L.LCU_FAST_ATANH):
+            m = L.Model(ctx, ["vecfn", "sersic"], IMG, IMG, flags=flags, ipp=[[0]*3, [1, 1, 0, 0, 0, 0, 0]])
+            assert m.rays_per_thread == 2
+            assert "warning" not in m.build_log
+    finally:
+        ctx.close()
