@@ -476,6 +476,30 @@ def test_random_models(gpu_ctx, seed, flags):
     assert np.array_equal(m.loglike_batch(P)[0], got)
 
 
+@pytest.mark.parametrize("seed", [2, 4, 8, 12, 14, 16])
+def test_random_models_with_image_plane_priors(gpu_ctx, seed):
+    """The same scenes with image-plane priors on every lensed source: the
+    generated set_params shoots the position through all lenses of the plane
+    (src/kernel.c:499-564; the oracle is pinned bit for bit on exactly these
+    configurations, tests/test_oracle.py)."""
+    cfg = H.random_config(seed)
+    seen_lens, flags = False, []
+    for o in cfg.objects:
+        info = O.object_info(o)
+        seen_lens = seen_lens or info["type"] == "L"
+        flags.append([int(info["type"] == "S" and seen_lens and p["type"] in (1, 2)) for p in info["params"]])
+    cfg.ipp = flags
+    assert any(any(f) for f in flags)
+    om = cfg.oracle()
+    m = cfg.product(gpu_ctx, flags=FAST)
+    _check_block(m, om, cfg, atol=1e-6)
+    out = m.render(cfg.params)
+    _check_images(out, cfg, om)
+    lnew = om.loglike(cfg.params)
+    got = m.loglike(cfg.params)
+    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew), f"{cfg.name}: lnew {got} vs {lnew}"
+
+
 def test_pixel_coordinate_system(gpu_ctx):
     """Image sections: origin and pixel scale (src/data.c:236-276) enter the
     pixel positions (kernel/lensed.cl:24) and scale the quadrature abscissae
