@@ -1,0 +1,668 @@
+"""A small PTX interpreter for straight-line float32 device functions.
+
+Test infrastructure (CPU only): it lets `tests/test_pair_math.py` run the PTX
+that NVRTC emits for shim.cuh's pair functions (`lcu_pf`: the same quantity for
+two rays in one 64-bit register, packed `.f32x2` arithmetic) next to the PTX of
+the scalar function each of them restates (libdevice's expf / logf / atanf /
+atanhf / atan2f / sincosf / powf as inlined by NVRTC), on the same inputs, and
+compare the results bit for bit -- without a GPU.
+
+Arithmetic follows the PTX ISA: IEEE-754 binary32 with the rounding mode the
+instruction names (exact rational arithmetic + one rounding), `.ftz` flushes
+subnormal inputs and results to signed zero, NaN results are the canonical
+0x7fffffff.  The special-function-unit approximations (`rcp/rsqrt/ex2/lg2
+.approx`) are NOT the hardware's tables: they are a deterministic stand-in
+(correctly rounded result with the last bit flipped by a hash of the argument
+bits), which is all a comparison of two instruction streams needs -- both must
+hand the unit the same bits to get the same bits back.  `sqrt.rn`, `div.rn` and
+`rcp.rn` are exact IEEE operations, as in PTX.
+
+Only the instructions that occur in those functions are implemented; anything
+else raises NotImplementedError with the offending line.
+"""
+from __future__ import annotations
+
+import math
+import re
+import struct
+from fractions import Fraction
+
+M32 = 0xFFFFFFFF
+M64 = 0xFFFFFFFFFFFFFFFF
+CANON_NAN = 0x7FFFFFFF
+
+
+# ---------------------------------------------------------------------------
+# binary32 helpers on bit patterns
+# ---------------------------------------------------------------------------
+def f2b(x: float) -> int:
+    return struct.unpack("<I", struct.pack("<f", x))[0]
+
+
+def b2f(b: int) -> float:
+    return struct.unpack("<f", struct.pack("<I", b & M32))[0]
+
+
+def d2b(x: float) -> int:
+    return struct.unpack("<Q", struct.pack("<d", x))[0]
+
+
+def b2d(b: int) -> float:
+    return struct.unpack("<d", struct.pack("<Q", b & M64))[0]
+
+
+def is_nan(b: int) -> bool:
+    return (b & 0x7F800000) == 0x7F800000 and (b & 0x007FFFFF) != 0
+
+
+def is_inf(b: int) -> bool:
+    return (b & 0x7FFFFFFF) == 0x7F800000
+
+
+def is_zero(b: int) -> bool:
+    return (b & 0x7FFFFFFF) == 0
+
+
+def ftz(b: int) -> int:
+    """flush a subnormal bit pattern to zero of the same sign"""
+    if (b & 0x7F800000) == 0:
+        return b & 0x80000000
+    return b
+
+
+def to_frac(b: int) -> Fraction:
+    s = -1 if b & 0x80000000 else 1
+    e = (b >> 23) & 0xFF
+    m = b & 0x007FFFFF
+    if e == 0:
+        return Fraction(s * m, 1 << 149)
+    return s * Fraction((1 << 23) | m) * Fraction(2) ** (e - 150)
+
+
+def round_frac(x: Fraction, mode: str = "rn", flush: bool = False, neg_zero: bool = False) -> int:
+    """exact rational -> binary32 bits under rounding mode rn / rz / rm / rp"""
+    if x == 0:
+        return 0x80000000 if neg_zero else 0
+    sign = 0x80000000 if x < 0 else 0
+    a = -x if x < 0 else x
+    # exponent e with 2^e <= a < 2^(e+1)
+    e = a.numerator.bit_length() - a.denominator.bit_length()
+    if Fraction(2) ** e > a:
+        e -= 1
+    elif Fraction(2) ** (e + 1) <= a:
+        e += 1
+    q = max(e, -126) - 23                         # weight of the last mantissa bit
+    scaled = a / (Fraction(2) ** q)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    up = False
+    if rem != 0:
+        if mode == "rn":
+            up = rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (n & 1))
+        elif mode == "rz":
+            up = False
+        elif mode == "rm":
+            up = bool(sign)
+        elif mode == "rp":
+            up = not sign
+        else:
+            raise NotImplementedError(mode)
+    if up:
+        n += 1
+    if n >= (1 << 24):
+        n >>= 1
+        q += 1
+    if n < (1 << 23):                             # subnormal (q == -149)
+        bits = sign | n
+        return (bits & 0x80000000) if flush else bits
+    ebits = q + 23 + 127
+    if ebits >= 255:
+        if mode == "rz" or (mode == "rm" and not sign) or (mode == "rp" and sign):
+            return sign | 0x7F7FFFFF
+        return sign | 0x7F800000
+    return sign | (ebits << 23) | (n & 0x007FFFFF)
+
+
+def _arith(op: str, a: int, b: int, c: int | None, mode: str, flush: bool) -> int:
+    """add / sub / mul / fma on bit patterns"""
+    if flush:
+        a, b = ftz(a), ftz(b)
+        if c is not None:
+            c = ftz(c)
+    if op == "sub":
+        b ^= 0x80000000
+        op = "add"
+    if is_nan(a) or is_nan(b) or (c is not None and is_nan(c)):
+        return CANON_NAN
+    if op == "add":
+        if is_inf(a) or is_inf(b):
+            if is_inf(a) and is_inf(b) and (a ^ b) & 0x80000000:
+                return CANON_NAN
+            return a if is_inf(a) else b
+        r = to_frac(a) + to_frac(b)
+        nz = False
+        if r == 0:                                # signed zero of an exact cancellation
+            if is_zero(a) and is_zero(b):
+                nz = bool(a & b & 0x80000000) if mode != "rm" else bool((a | b) & 0x80000000)
+            else:
+                nz = mode == "rm"
+        return round_frac(r, mode, flush, nz)
+    if op == "mul":
+        sign = (a ^ b) & 0x80000000
+        if is_inf(a) or is_inf(b):
+            if is_zero(a) or is_zero(b):
+                return CANON_NAN
+            return sign | 0x7F800000
+        return round_frac(to_frac(a) * to_frac(b), mode, flush, bool(sign))
+    if op == "fma":
+        psign = (a ^ b) & 0x80000000
+        if is_inf(a) or is_inf(b):
+            if is_zero(a) or is_zero(b):
+                return CANON_NAN
+            if is_inf(c) and (c ^ psign) & 0x80000000:
+                return CANON_NAN
+            return psign | 0x7F800000
+        if is_inf(c):
+            return c
+        p = to_frac(a) * to_frac(b)
+        r = p + to_frac(c)
+        nz = False
+        if r == 0:
+            if p == 0 and is_zero(c):
+                nz = bool(psign and (c & 0x80000000)) if mode != "rm" else bool(psign or (c & 0x80000000))
+            else:
+                nz = mode == "rm"
+        return round_frac(r, mode, flush, nz)
+    raise NotImplementedError(op)
+
+
+def _hash_bit(b: int) -> int:
+    return ((b * 2654435761) >> 13) & 1
+
+
+def _approx(kind: str, a: int, flush: bool) -> int:
+    """deterministic stand-in for a special-function-unit approximation"""
+    if flush:
+        a = ftz(a)
+    if is_nan(a):
+        return CANON_NAN
+    x = b2f(a)
+    neg = bool(a & 0x80000000)
+    if kind == "rcp":
+        if is_zero(a):
+            return (a & 0x80000000) | 0x7F800000
+        if is_inf(a):
+            return a & 0x80000000
+        r = round_frac(1 / to_frac(a), "rn", flush)
+    elif kind == "rsqrt":
+        if is_zero(a):
+            return (a & 0x80000000) | 0x7F800000
+        if neg:
+            return CANON_NAN
+        if is_inf(a):
+            return 0
+        r = f2b(1.0 / math.sqrt(x))
+    elif kind == "ex2":
+        if is_inf(a):
+            return 0 if neg else 0x7F800000
+        if x > 128.0:
+            return 0x7F800000
+        if x < -150.0:
+            return 0
+        r = f2b(2.0 ** x)
+    elif kind == "lg2":
+        if is_zero(a):
+            return 0xFF800000
+        if neg:
+            return CANON_NAN
+        if is_inf(a):
+            return a
+        r = f2b(math.log2(x))
+    else:
+        raise NotImplementedError(kind)
+    if flush:
+        r = ftz(r)
+    if (r & 0x7F800000) not in (0, 0x7F800000):   # keep zeros / infinities / subnormals as they are
+        r ^= _hash_bit(a)
+    return r
+
+
+def _ieee(kind: str, a: int, b: int | None, flush: bool) -> int:
+    """sqrt.rn / div.rn / rcp.rn"""
+    if flush:
+        a = ftz(a)
+        if b is not None:
+            b = ftz(b)
+    if is_nan(a) or (b is not None and is_nan(b)):
+        return CANON_NAN
+    if kind == "sqrt":
+        if is_zero(a):
+            return a
+        if a & 0x80000000:
+            return CANON_NAN
+        if is_inf(a):
+            return a
+        fr = to_frac(a)
+        # integer square root at 2x48 extra bits decides the rounding exactly
+        k = 160
+        n = (fr * Fraction(2) ** (2 * k))
+        root = math.isqrt(n.numerator // n.denominator)
+        exact = root * root == n and n.denominator == 1
+        r = Fraction(root, 1 << k)
+        if not exact:
+            r += Fraction(1, 1 << (k + 2))        # sticky: strictly between root and root + 1
+        return round_frac(r, "rn", flush)
+    if kind == "rcp":
+        b = a
+        a = 0x3F800000
+    sign = (a ^ b) & 0x80000000
+    if is_inf(a):
+        return CANON_NAN if is_inf(b) else sign | 0x7F800000
+    if is_inf(b):
+        return sign
+    if is_zero(b):
+        return CANON_NAN if is_zero(a) else sign | 0x7F800000
+    return round_frac(to_frac(a) / to_frac(b), "rn", flush, bool(sign))
+
+
+def _cmp_f(op: str, a: int, b: int, flush: bool) -> bool:
+    if flush:
+        a, b = ftz(a), ftz(b)
+    nan = is_nan(a) or is_nan(b)
+    if op == "num":
+        return not nan
+    if op == "nan":
+        return nan
+    base = {"eq": "eq", "ne": "ne", "lt": "lt", "le": "le", "gt": "gt", "ge": "ge",
+            "equ": "eq", "neu": "ne", "ltu": "lt", "leu": "le", "gtu": "gt", "geu": "ge"}[op]
+    if nan:
+        return op in ("equ", "neu", "ltu", "leu", "gtu", "geu")
+    x, y = to_frac(a), to_frac(b)
+    return {"eq": x == y, "ne": x != y, "lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y}[base]
+
+
+def _s32(v: int) -> int:
+    v &= M32
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def _s64(v: int) -> int:
+    v &= M64
+    return v - (1 << 64) if v & (1 << 63) else v
+
+
+def _round_int(fr: Fraction, mode: str) -> int:
+    fl = fr.numerator // fr.denominator
+    if mode == "rzi":
+        return fl if fr >= 0 else -((-fr).numerator // (-fr).denominator)
+    if mode == "rmi":
+        return fl
+    if mode == "rpi":
+        return fl if fr == fl else fl + 1
+    if mode == "rni":
+        rem = fr - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (fl & 1)):
+            return fl + 1
+        return fl
+    raise NotImplementedError(mode)
+
+
+# ---------------------------------------------------------------------------
+# the interpreter
+# ---------------------------------------------------------------------------
+class Function:
+    def __init__(self, name, params, body):
+        self.name, self.params, self.body = name, params, body
+        self.labels = {}
+        self.insns = []
+        for line in body:
+            m = re.match(r"^(\$?[\w$]+):$", line)
+            if m:
+                self.labels[m.group(1)] = len(self.insns)
+            else:
+                self.insns.append(line)
+
+
+class Module:
+    """entries and initialised global arrays of one PTX text"""
+
+    def __init__(self, ptx: str):
+        self.functions = {}
+        self.globals = {}                          # name -> (address, bytes)
+        self._next_global = 0x10000000
+        text = re.sub(r"//[^\n]*", "", ptx)
+        for m in re.finditer(r"\.global\s+\.align\s+\d+\s+\.b8\s+(\w+)\[(\d+)\]\s*=\s*\{([^}]*)\};", text):
+            data = bytes(int(v) for v in m.group(3).split(","))
+            self.globals[m.group(1)] = (self._next_global, data)
+            self._next_global += (len(data) + 255) & ~255
+        for m in re.finditer(r"\.visible\s+\.entry\s+(\w+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
+            params = re.findall(r"(\w+_param_\d+)", m.group(2))
+            body = []
+            for raw in m.group(3).split("\n"):
+                line = raw.strip()
+                if not line or line.startswith(".reg") or line.startswith(".pragma") or line.startswith(".loc") \
+                        or line.startswith(".local"):
+                    continue
+                body.append(line)
+            self.functions[m.group(1)] = Function(m.group(1), params, body)
+
+    def run(self, name: str, inputs, n_out: int, max_steps: int = 20000):
+        """run entry `name(float* out, const float* in0, const float* in1, ...)`;
+        inputs: one list of uint32 bit patterns per input pointer; returns n_out words"""
+        fn = self.functions[name]
+        mem = {}
+        for addr, data in self.globals.values():
+            for i in range(0, len(data), 4):
+                mem[addr + i] = int.from_bytes(data[i:i + 4], "little")
+        out_addr = 0x1000
+        ptrs = [out_addr]
+        for k, words in enumerate(inputs):
+            base = 0x2000 + 0x1000 * k
+            ptrs.append(base)
+            for i, w in enumerate(words):
+                mem[base + 4 * i] = w & M32
+        assert len(ptrs) == len(fn.params), (name, len(ptrs), fn.params)
+        env = dict(zip(fn.params, ptrs))
+        _Machine(self, fn, env, mem).execute(max_steps)
+        return [mem.get(out_addr + 4 * i) for i in range(n_out)]
+
+
+class _Machine:
+    def __init__(self, module, fn, params, mem):
+        self.module, self.fn, self.params, self.mem = module, fn, params, mem
+        self.reg = {}
+        self.local_base = 0x20000000
+
+    # operand access -------------------------------------------------------
+    def val(self, tok: str, width: int = 32) -> int:
+        tok = tok.strip()
+        if tok.startswith("%"):
+            return self.reg[tok]
+        if tok.startswith("0f") or tok.startswith("0F"):
+            return int(tok[2:], 16)
+        if tok.startswith("0d") or tok.startswith("0D"):
+            return int(tok[2:], 16)
+        if tok in self.module.globals:
+            return self.module.globals[tok][0]
+        if tok.startswith("__local_depot"):
+            return self.local_base
+        if re.match(r"^-?(0x[0-9a-fA-F]+|\d+)$", tok):
+            return int(tok, 0) & (M64 if width == 64 else M32)
+        raise NotImplementedError("operand " + tok)
+
+    def pred(self, tok: str) -> bool:
+        tok = tok.strip()
+        if tok.startswith("!"):
+            return not self.reg[tok[1:]]
+        return bool(self.reg[tok])
+
+    def addr(self, tok: str) -> int:
+        m = re.match(r"^\[([^\]+]+)(\+(-?\d+))?\]$", tok.strip())
+        base = m.group(1)
+        off = int(m.group(3)) if m.group(3) else 0
+        if base in self.params:
+            return ("param", base)
+        return (self.val(base, 64) + off) & M64
+
+    # execution ------------------------------------------------------------
+    def execute(self, max_steps: int):
+        pc, steps = 0, 0
+        insns = self.fn.insns
+        while pc < len(insns):
+            steps += 1
+            if steps > max_steps:
+                raise RuntimeError("step limit in " + self.fn.name)
+            line = insns[pc].rstrip(";").strip()
+            pc += 1
+            guard = re.match(r"^@(!?%p\d+)\s+(.*)$", line)
+            if guard:
+                if not self.pred(guard.group(1)):
+                    continue
+                line = guard.group(2)
+            op, _, rest = line.partition(" ")
+            rest = rest.strip()
+            if op in ("ret", "exit"):
+                return
+            if op in ("bra", "bra.uni"):
+                pc = self.fn.labels[rest]
+                continue
+            self.step(op, rest, line)
+
+    def step(self, op: str, rest: str, line: str):
+        parts = op.split(".")
+        name, mods = parts[0], parts[1:]
+        # operands: split on commas outside braces
+        args = [a.strip() for a in re.split(r",\s*(?![^{]*\})", rest)]
+        R = self.reg
+        flush = "ftz" in mods
+        mode = next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn")
+        typ = mods[-1] if mods else ""
+
+        if name == "ld":
+            if mods[0] == "param":
+                R[args[0]] = self.params[re.match(r"^\[(\w+)\]$", args[1]).group(1)]
+                return
+            a = self.addr(args[1])
+            wide = typ in ("u64", "b64", "s64", "f64")
+            word = (lambda at: self.mem.get(at, 0) | (self.mem.get(at + 4, 0) << 32)) if wide else (lambda at: self.mem.get(at, 0))
+            if args[0].startswith("{"):            # ld.global.v2 / .v4
+                for i, d in enumerate(t.strip() for t in args[0].strip("{}").split(",")):
+                    R[d] = word(a + i*(8 if wide else 4))
+            else:
+                R[args[0]] = word(a)
+            return
+        if name == "st":
+            a = self.addr(args[0])
+            self.mem[a] = self.val(args[1], 64) & M32
+            return
+        if name == "cvta":
+            R[args[0]] = self.val(args[1], 64)
+            return
+        if name == "mov":
+            d, s = args
+            if d.startswith("{"):
+                lo, hi = [t.strip() for t in d.strip("{}").split(",")]
+                v = self.val(s, 64)
+                R[lo], R[hi] = v & M32, (v >> 32) & M32
+            elif s.startswith("{"):
+                lo, hi = [t.strip() for t in s.strip("{}").split(",")]
+                R[d] = (self.val(lo) & M32) | ((self.val(hi) & M32) << 32)
+            else:
+                R[d] = self.val(s, 64 if typ in ("b64", "u64", "s64", "f64") else 32)
+            return
+        if name in ("add", "sub", "mul", "fma") and typ == "f32":
+            c = self.val(args[3]) if name == "fma" else None
+            R[args[0]] = _arith(name, self.val(args[1]), self.val(args[2]), c, mode, flush)
+            return
+        if name in ("add", "sub", "mul", "fma") and typ == "f32x2":
+            a, b = self.val(args[1], 64), self.val(args[2], 64)
+            c = self.val(args[3], 64) if name == "fma" else None
+            out = 0
+            for sh in (0, 32):
+                cc = ((c >> sh) & M32) if c is not None else None
+                out |= _arith(name, (a >> sh) & M32, (b >> sh) & M32, cc, mode, flush) << sh
+            R[args[0]] = out
+            return
+        if name == "mul" and typ == "f64":
+            R[args[0]] = d2b(b2d(self.val(args[1], 64)) * b2d(self.val(args[2], 64)))
+            return
+        if name in ("abs", "neg") and typ == "f32":
+            v = self.val(args[1])
+            if flush:
+                v = ftz(v)
+            R[args[0]] = (v & 0x7FFFFFFF) if name == "abs" else (v ^ 0x80000000)
+            return
+        if name == "copysign":
+            R[args[0]] = (self.val(args[1]) & 0x80000000) | (self.val(args[2]) & 0x7FFFFFFF)
+            return
+        if name in ("max", "min") and typ == "f32":
+            a, b = self.val(args[1]), self.val(args[2])
+            if flush:
+                a, b = ftz(a), ftz(b)
+            if is_nan(a) and is_nan(b):
+                R[args[0]] = CANON_NAN
+            elif is_nan(a):
+                R[args[0]] = b
+            elif is_nan(b):
+                R[args[0]] = a
+            else:
+                x, y = to_frac(a), to_frac(b)
+                if x == y:                        # +0 / -0: max prefers +0, min -0
+                    R[args[0]] = (a & b) if name == "max" else (a | b)
+                else:
+                    R[args[0]] = (a if x > y else b) if name == "max" else (a if x < y else b)
+            return
+        if name in ("max", "min") and typ in ("u32", "s32"):
+            cv = _s32 if typ == "s32" else (lambda v: v & M32)
+            a, b = cv(self.val(args[1])), cv(self.val(args[2]))
+            R[args[0]] = (max(a, b) if name == "max" else min(a, b)) & M32
+            return
+        if name in ("rcp", "rsqrt", "ex2", "lg2") and "approx" in mods:
+            R[args[0]] = _approx(name, self.val(args[1]), flush)
+            return
+        if name == "sqrt" and "rn" in mods:
+            R[args[0]] = _ieee("sqrt", self.val(args[1]), None, flush)
+            return
+        if name == "rcp" and "rn" in mods:
+            R[args[0]] = _ieee("rcp", self.val(args[1]), None, flush)
+            return
+        if name == "div" and "rn" in mods and typ == "f32":
+            R[args[0]] = _ieee("div", self.val(args[1]), self.val(args[2]), flush)
+            return
+        if name == "setp":
+            cmp = mods[0]
+            a_tok, b_tok = args[1], args[2]
+            if typ == "f32":
+                R[args[0]] = _cmp_f(cmp, self.val(a_tok), self.val(b_tok), flush)
+            else:
+                w = 64 if typ.endswith("64") else 32
+                a, b = self.val(a_tok, w), self.val(b_tok, w)
+                if typ.startswith("s"):
+                    a, b = (_s64(a), _s64(b)) if w == 64 else (_s32(a), _s32(b))
+                R[args[0]] = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b,
+                              "lo": a < b, "ls": a <= b, "hi": a > b, "hs": a >= b}[cmp]
+            return
+        if name == "selp":
+            R[args[0]] = self.val(args[1], 64) if self.pred(args[3]) else self.val(args[2], 64)
+            if typ in ("f32", "b32", "u32", "s32"):
+                R[args[0]] &= M32
+            return
+        if name in ("and", "or", "xor") and typ == "pred":
+            a, b = self.pred(args[1]), self.pred(args[2])
+            R[args[0]] = {"and": a and b, "or": a or b, "xor": a != b}[name]
+            return
+        if name == "not" and typ == "pred":
+            R[args[0]] = not self.pred(args[1])
+            return
+        if name in ("and", "or", "xor"):
+            w = 64 if typ == "b64" else 32
+            a, b = self.val(args[1], w), self.val(args[2], w)
+            R[args[0]] = {"and": a & b, "or": a | b, "xor": a ^ b}[name] & (M64 if w == 64 else M32)
+            return
+        if name == "not":
+            w = 64 if typ == "b64" else 32
+            R[args[0]] = ~self.val(args[1], w) & (M64 if w == 64 else M32)
+            return
+        if name == "shl":
+            w = 64 if typ == "b64" else 32
+            n = self.val(args[2]) & M32
+            R[args[0]] = (self.val(args[1], w) << n) & (M64 if w == 64 else M32) if n < w else 0
+            return
+        if name == "shr":
+            w = 64 if typ.endswith("64") else 32
+            n = min(self.val(args[2]) & M32, w)
+            v = self.val(args[1], w)
+            if typ.startswith("s"):
+                v = _s64(v) if w == 64 else _s32(v)
+                n = min(n, w - 1)
+            R[args[0]] = (v >> n) & (M64 if w == 64 else M32)
+            return
+        if name == "shf":                          # shf.l.wrap.b32 d, lo, hi, n
+            lo, hi, n = self.val(args[1]), self.val(args[2]), self.val(args[3]) & 31
+            v = ((hi << 32) | lo) << n if mods[0] == "l" else ((hi << 32) | lo) >> n
+            R[args[0]] = ((v >> 32) & M32) if mods[0] == "l" else (v & M32)
+            return
+        if name in ("add", "sub") and typ in ("s32", "u32", "s64", "u64"):
+            w = 64 if typ.endswith("64") else 32
+            a, b = self.val(args[1], w), self.val(args[2], w)
+            R[args[0]] = (a + b if name == "add" else a - b) & (M64 if w == 64 else M32)
+            return
+        if name == "neg" and typ == "s32":
+            R[args[0]] = (-self.val(args[1])) & M32
+            return
+        if name == "mul" and "wide" in mods:
+            a, b = self.val(args[1]), self.val(args[2])
+            if typ == "s32":
+                a, b = _s32(a), _s32(b)
+            R[args[0]] = (a * b) & M64
+            return
+        if name == "mad" and "wide" in mods:
+            a, b = self.val(args[1]), self.val(args[2])
+            if typ == "s32":
+                a, b = _s32(a), _s32(b)
+            R[args[0]] = (a * b + self.val(args[3], 64)) & M64
+            return
+        if name == "mul" and "lo" in mods:
+            R[args[0]] = (self.val(args[1]) * self.val(args[2])) & M32
+            return
+        if name == "cvt":
+            R[args[0]] = self.cvt(mods, self.val(args[1], 64))
+            return
+        raise NotImplementedError(line)
+
+    def cvt(self, mods, v: int) -> int:
+        dst, src = mods[-2], mods[-1]
+        flush = "ftz" in mods
+        sat = "sat" in mods
+        imode = next((m for m in mods if m in ("rni", "rzi", "rmi", "rpi")), None)
+        if src == "f32" and dst == "f32":
+            v &= M32
+            if flush:
+                v = ftz(v)
+            if is_nan(v):
+                return 0 if sat else CANON_NAN
+            if imode and not is_inf(v):
+                fr = to_frac(v)
+                n = _round_int(fr, imode)
+                v = round_frac(Fraction(n), "rn", False, bool(v & 0x80000000))
+            if sat:
+                fr = Fraction(0) if is_zero(v) else (Fraction(2) if is_inf(v) and not v & 0x80000000 else (Fraction(-1) if is_inf(v) else to_frac(v)))
+                if fr <= 0:
+                    return 0
+                if fr >= 1:
+                    return 0x3F800000
+            return v
+        if src == "f32" and dst in ("s32", "u32"):
+            v &= M32
+            if flush:
+                v = ftz(v)
+            if is_nan(v):
+                return 0
+            lo, hi = ((-(1 << 31), (1 << 31) - 1) if dst == "s32" else (0, M32))
+            if is_inf(v):
+                return (lo if v & 0x80000000 else hi) & M32
+            n = _round_int(to_frac(v), imode)
+            return max(lo, min(hi, n)) & M32
+        if src in ("s32", "u32") and dst == "f32":
+            n = _s32(v) if src == "s32" else v & M32
+            mode = next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn")
+            return round_frac(Fraction(n), mode)
+        if src == "u32" and dst == "u64":
+            return v & M32
+        if src == "s32" and dst == "s64":
+            return _s32(v) & M64
+        if src == "s64" and dst == "f64":
+            return d2b(float(_s64(v)))            # |v| < 2^63: Python rounds to nearest even
+        if src == "f64" and dst == "f32":
+            x = b2d(v)
+            if x != x:
+                return CANON_NAN
+            if math.isinf(x):
+                return 0x7F800000 | (0x80000000 if x < 0 else 0)
+            return round_frac(Fraction(x), "rn", flush, math.copysign(1.0, x) < 0)
+        if src == "f32" and dst == "f64":
+            v &= M32
+            if flush:
+                v = ftz(v)
+            return d2b(b2f(v))
+        raise NotImplementedError("cvt." + ".".join(mods))
