@@ -40,7 +40,7 @@ extern "C" __global__ void p_##name(float* o, const float* a, const float* b) \
 { lcu_pf r = fn(lcu_pf(a[0], a[1]), lcu_pf(b[0], b[1])); o[0] = r.lo(); o[1] = r.hi(); }
 K1(sqrt, sqrt) K1(atan, atan) K1(exp, exp) K1(log, log) K1(atanh, atanh)
 K1(fast_exp, lcu_fast_exp) K1(fast_log, lcu_fast_log) K1(fast_atanh, lcu_fast_atanh)
-K2(atan2, atan2) K2(powr, powr) K2(pow, pow)
+K2(atan2, atan2) K2(powr, powr) K2(pow, pow) K1(sin, sin) K1(cos, cos)
 extern "C" __global__ void s_sincos(float* o, const float* a) { float c; o[0] = sincos(a[0], &c); o[1] = c; }
 extern "C" __global__ void p_sincos(float* o, const float* a)
 { lcu_pf c; lcu_pf r = sincos(lcu_pf(a[0], a[1]), &c); o[0] = r.lo(); o[1] = c.lo(); o[2] = r.hi(); o[3] = c.hi(); }
@@ -154,6 +154,18 @@ def test_pair_sincos_same_bits(ptx_packed):
     _compare(M, "sincos", 1, 2, draws)
 
 
+@pytest.mark.parametrize("name", ["sin", "cos"])
+def test_pair_sin_cos_same_bits(ptx_packed, name):
+    M = E.Module(ptx_packed)
+    rng = random.Random(16)
+    draws = [((_u(rng, -7, 7), _u(rng, -7, 7)),) for _ in range(200)]
+    draws += [((_lu(rng, 1e-40, 1e5), _lu(rng, 1e-10, 1e6)),) for _ in range(200)]
+    draws += [((rng.choice(SPECIAL), _u(rng, -4, 4)),) for _ in range(80)]
+    draws += [((_u(rng, -4, 4), _lu(rng, 1e5, 1e38)),) for _ in range(80)]
+    draws += [((rng.choice(SPECIAL), rng.choice(SPECIAL)),) for _ in range(80)]
+    _compare(M, name, 1, 1, draws)
+
+
 @pytest.mark.parametrize("name", ["powr", "pow"])
 def test_pair_pow_same_bits(ptx_packed, name):
     M = E.Module(ptx_packed)
@@ -215,7 +227,7 @@ def test_comparison_is_sensitive(ptx_packed):
 def test_default_build_calls_libdevice_lane_by_lane(ptx_default, ptx_packed):
     """the switch is off by default: without it atan2 / sincos / powr of pairs
     contain no packed instruction, with it they do"""
-    for name in ("atan2", "sincos", "powr"):
+    for name in ("atan2", "sincos", "powr", "sin", "cos"):
         for ptx, packed in ((ptx_default, False), (ptx_packed, True)):
             entry = re.search(r"\.visible\s+\.entry\s+p_%s\b.*?\n\}" % name, ptx, re.S).group(0)
             assert ("f32x2" in entry) == packed, (name, packed)
