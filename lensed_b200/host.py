@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -188,15 +189,22 @@ def read_ini(path: str, ctx: Context) -> Config:
     nplanes, typ = 0, None
     with open(path) as f:
         for lineno, raw in enumerate(f, 1):
-            line = raw.split(";")[0].strip()
+            # src/input/ini.c:16-25,152-218: a line ends at ';' or '#', a group is
+            # [name], name and value are split at the first '=' or ':'
+            line = re.split(r"[;#]", raw, maxsplit=1)[0].strip()
             if not line:
                 continue
             if line.startswith("["):
-                grp = line.strip("[]").strip()
+                if not line.endswith("]"):
+                    raise ValueError(f"{path}:{lineno}: missing closing ']' character for group")
+                grp = line[1:-1].strip()
+                if grp not in ("options", "objects", "priors", "labels"):
+                    raise ValueError(f"{path}:{lineno}: unknown group: {grp}")
                 continue
-            if "=" not in line:
-                raise ValueError(f"{path}:{lineno}: expected name = value")
-            name, value = (s.strip() for s in line.split("=", 1))
+            parts = re.split(r"[=:]", line, maxsplit=1)
+            if len(parts) != 2:
+                raise ValueError(f"{path}:{lineno}: line does not assign anything to \"{line}\"")
+            name, value = (s.strip() for s in parts)
             if grp == "options":
                 options[name] = value
             elif grp == "objects":

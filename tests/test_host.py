@@ -115,6 +115,51 @@ def test_ini_errors(compile_ctx, tmp_path):
         assert msg in str(e.value)
 
 
+def test_ini_syntax_of_the_reference(compile_ctx, tmp_path):
+    """src/input/ini.c:16-25: '=' or ':' assigns, ';' or '#' ends a line,
+    groups are [name] with optional blanks, unknown / unclosed groups are errors."""
+    path = _write_case(tmp_path)
+    text = open(path).read()
+    alt = (text.replace("gain   = 1800", "gain   : 1800   # electrons per count")
+               .replace("host.x     = unif 55 65", "host.x: unif 55 65 ; centre")
+               .replace("[priors]", "[ priors ]"))
+    open(path, "w").write(alt)
+    cfg, _, like = host.build(path, compile_ctx)
+    assert cfg.options["gain"] == "1800" and like.npars == 7 + 5 + 7 + 3
+    assert cfg.objects[0].params[0].prior.apply(0.5) == 60.0
+    for bad, msg in ((text.replace("[priors]", "[priors"), "missing closing ']'"),
+                     (text.replace("[labels]", "[lables]"), "unknown group: lables"),
+                     (text.replace("rule   = g3k7", "rule g3k7"), "does not assign anything")):
+        open(path, "w").write(bad)
+        with pytest.raises(ValueError) as e:
+            host.build(path, compile_ctx)
+        assert msg in str(e.value)
+
+
+REFERENCE = os.environ.get("LENSED_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "tests")), reason="reference tree not present")
+def test_reads_every_ini_file_of_the_reference(compile_ctx):
+    """the reference's three examples and 16 test configurations, unmodified:
+    objects, priors (incl. `wrap` / `image` keywords) and options come out as the files say"""
+    import glob
+    files = sorted(glob.glob(os.path.join(REFERENCE, "examples", "*.ini")) + glob.glob(os.path.join(REFERENCE, "tests", "*", "*.ini")))
+    assert len(files) == 19
+    for path in files:
+        cfg = host.read_ini(path, compile_ctx)
+        assert cfg.objects and "image" in cfg.options, path
+        for p in cfg.parameters:
+            assert p.prior is not None, (path, p.id)
+        name = os.path.basename(path)[:-4]
+        if "tests" in path.split(os.sep):
+            assert all(p.prior.pseudo for p in cfg.parameters), path        # fully specified models
+            assert any(o.name == name.split("-")[0] for o in cfg.objects), path   # tests/lens/sie.ini tests `sie`
+    cfg = host.read_ini(os.path.join(REFERENCE, "examples", "test_sersic_bulge.ini"), compile_ctx)
+    by_id = {p.id: p for p in cfg.parameters}
+    assert by_id["source.x"].ipp and by_id["source.y"].ipp and by_id["lens.pa"].wrap and not by_id["lens.x"].ipp
+
+
 @pytest.mark.gpu
 def test_reference_style_known_answer_run(gpu_ctx, tmp_path):
     """tests/lens/sie.ini of the reference, reproduced: all parameters fixed,
