@@ -128,13 +128,17 @@ def read_prior(spec: str) -> Prior:
             pass
     if not args:
         raise ValueError("empty prior")
-    if args[0] == "unif" and len(args) == 3:
-        return Uniform(float(args[1]), float(args[2]))
-    if args[0] == "norm" and len(args) == 3:
-        return Normal(float(args[1]), float(args[2]))
-    if args[0] == "delta" and len(args) == 2:
-        return Delta(float(args[1]))
-    raise ValueError(f"invalid prior definition: {spec}")
+    # named priors: the list is searched from its second entry, so that "delta"
+    # is reachable only as a bare number (src/prior.c:119-133)
+    kinds = {"unif": Uniform, "norm": Normal}
+    if args[0] not in kinds:
+        raise ValueError(f"unknown prior: {args[0]}")
+    try:
+        if len(args) != 3:
+            raise ValueError
+        return kinds[args[0]](float(args[1]), float(args[2]))
+    except ValueError:
+        raise ValueError(f"invalid prior definition: {spec}") from None
 
 
 # ---------------------------------------------------------------------------
@@ -342,6 +346,12 @@ def build(path: str, ctx: Context, **model_kw):
     from . import workloads
     cfg = read_ini(path, ctx)
     opt = cfg.options
+    # src/input.c:230-238: `image` is required, `gain` unless a weight map is given, and some objects
+    for name in ("image",) + (() if "weight" in opt else ("gain",)):
+        if name not in opt:
+            raise ValueError(f"missing required option: {name}")
+    if not cfg.objects:
+        raise ValueError("no objects were given (check [objects] section)")
 
     def rel(p):
         return p if os.path.isabs(p) else os.path.join(cfg.basedir, p)
@@ -362,7 +372,7 @@ def build(path: str, ctx: Context, **model_kw):
     if "weight" in opt:
         weight = value_or_file(opt["weight"])
     else:
-        gain = value_or_file(opt.get("gain", "1"))
+        gain = value_or_file(opt["gain"])
         # make_weight(), src/data.c:314-330
         weight = (gain.astype(np.float64)/(image.astype(np.float64) + float(opt.get("offset", 0)))).astype(np.float32)
     if "xweight" in opt:

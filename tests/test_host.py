@@ -69,8 +69,11 @@ def test_priors():
     assert abs(n.apply(0.8413447) - (-5 + 2)) < 2e-3          # +1 sigma
     assert n.apply(0.1) == -10 - n.apply(0.9)                 # antisymmetric about the mean
     assert (n.lower(), n.upper()) == (-19, 9)
-    with pytest.raises(ValueError):
-        host.read_prior("cauchy 0 1")
+    for spec, msg in (("cauchy 0 1", "unknown prior: cauchy"), ("delta 1", "unknown prior: delta"),
+                      ("unif 1", "invalid prior definition"), ("norm 0 x", "invalid prior definition")):
+        with pytest.raises(ValueError) as e:                  # src/prior.c:119-147
+            host.read_prior(spec)
+        assert msg in str(e.value)
 
 
 def test_ini_parameter_map_and_transform(compile_ctx, tmp_path):
@@ -108,7 +111,10 @@ def test_ini_errors(compile_ctx, tmp_path):
     for bad, msg in ((text.replace("lens.q     = unif 0.1 1", "lens.q     = unif 2 3"), "prior does not include parameter bounds"),
                      (text.replace("sky    = sky", "sky    = sky\nlens2 = sis\nsrc2 = gauss\nlens3 = sis"), "multiple lensing planes"),
                      (text.replace("host.x     = unif 55 65", "nobody.x = 1"), "unknown object"),
-                     (text.replace("sky.bg     = unif 0 1", ""), "missing prior: sky.bg")):
+                     (text.replace("sky.bg     = unif 0 1", ""), "missing prior: sky.bg"),
+                     (text.replace("gain   = 1800", ""), "missing required option: gain"),
+                     (text.replace("image  = img.fits", ""), "missing required option: image"),
+                     (text.split("[objects]")[0], "no objects were given")):
         open(path, "w").write(bad)
         with pytest.raises(ValueError) as e:
             host.build(path, compile_ctx)
