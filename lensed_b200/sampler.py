@@ -245,7 +245,7 @@ def _box_draw(pts: np.ndarray, n: int, enlarge: float, rng) -> np.ndarray:
 def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int, *, nlive: int = 300,
                   batch: int = 64, tol: float = 0.1, eff: float = 0.8, seed: int = 0, maxiter: int = 0,
                   transform: Optional[Callable[[np.ndarray], np.ndarray]] = None, split: bool = False,
-                  method: str = "auto", walks: int = 0,
+                  method: str = "auto", walks: int = 0, wrap: Optional[Sequence[bool]] = None,
                   callback: Optional[Callable[[dict], None]] = None, update_interval: int = 0) -> NestedResult:
     """Nested sampling of a likelihood over the unit cube [0,1)^ndims.
 
@@ -257,6 +257,14 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     tol           : stop when the live points can raise ln Z by less than this
     eff           : target efficiency; the bound's volume is enlarged by 1/eff
     maxiter       : stop after this many dead points (0 = no limit)
+    wrap          : per dimension, whether it is periodic (the `wrap` keyword of
+                    a prior, handed to MultiNest as pWrap by src/lensed.c:1254-1259).
+                    The circle of a periodic dimension is cut opposite the live
+                    points before every step, so that a posterior straddling
+                    0 / 1 (a position angle near 0 = 180 degrees) is bounded by one
+                    small ellipsoid instead of one as wide as the cube; random-walk
+                    steps wrap around.  The cut is a measure-preserving
+                    re-parametrisation: draws stay uniform inside the contour.
     method        : how new points are drawn inside the likelihood contour.
                     "reject": uniform draws from the ellipsoidal bound (exact, but the
                     acceptance falls to 1e-3 and below for curved posteriors in >~ 10
@@ -286,6 +294,18 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
     if walks == 0:
         walks = max(25, 8*ndims)
     rng = np.random.default_rng(seed)
+    wrap_idx = np.nonzero(np.asarray(wrap, dtype=bool))[0] if wrap is not None else np.empty(0, dtype=int)
+    if wrap_idx.size and wrap_idx.max() >= ndims:
+        raise ValueError("nested_sample: wrap has more entries than there are dimensions")
+
+    def cut() -> np.ndarray:
+        """offset per dimension that moves the cut of every periodic dimension
+        half a turn away from the circular mean of the live points"""
+        off = np.zeros(ndims)
+        ang = 2.0*math.pi*live_u[:, wrap_idx]
+        mean = np.arctan2(np.sin(ang).mean(axis=0), np.cos(ang).mean(axis=0))/(2.0*math.pi)
+        off[wrap_idx] = (mean - 0.5) % 1.0
+        return off
 
     nan_points = 0
 
@@ -348,7 +368,7 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         lmin0 = live_l.min()
         start = rng.integers(nlive, size=nw)
         u, ll = live_u[start].copy(), live_l[start].copy()
-        cov = np.cov(live_u, rowvar=False).reshape(ndims, ndims)
+        cov = np.cov((live_u - cut()) % 1.0 if wrap_idx.size else live_u, rowvar=False).reshape(ndims, ndims)
         w, v = np.linalg.eigh(cov)
         w = np.maximum(w, max(w.max(), 1e-300)*1e-12)
         chol = np.linalg.cholesky((v*w) @ v.T)
@@ -356,6 +376,8 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         nacc = 0
         for _ in range(walks):
             prop = u + step_scale*(rng.standard_normal((nw, ndims)) @ chol.T)
+            if wrap_idx.size:
+                prop[:, wrap_idx] %= 1.0
             inside = np.all((prop >= 0.0) & (prop < 1.0), axis=1)
             if inside.any():
                 lp = evaluate(prop[inside])
@@ -384,7 +406,9 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
         else:
             # bound from the current live points; while it is no smaller than the
             # cube itself, draw from the cube
-            bound = _Bound(live_u, enlarge, rng, split, logx)
+            off = cut() if wrap_idx.size else None
+            pts = (live_u - off) % 1.0 if wrap_idx.size else live_u
+            bound = _Bound(pts, enlarge, rng, split, logx)
             if bound.logvol >= 0.0:
                 cand = rng.random((batch, ndims))
             else:
@@ -392,7 +416,10 @@ def nested_sample(loglike_batch: Callable[[np.ndarray], np.ndarray], ndims: int,
                     cand = bound.draw(batch, rng)
                 except RuntimeError:
                     # posterior pressed into a corner of the prior in many dimensions
-                    cand = _box_draw(live_u, batch, enlarge, rng)
+                    cand = _box_draw(pts, batch, enlarge, rng)
+                if wrap_idx.size:
+                    cand = (cand + off) % 1.0
+                    cand[cand >= 1.0] = 0.0       # (x + off) % 1 can round up to 1
             cl = evaluate(cand)
             nevals += batch
             nbatches += 1
@@ -467,6 +494,8 @@ def run(like, *, nlive: int = 300, batch: int = 64, tol: float = 0.1, eff: float
     def lb(cubes: np.ndarray) -> np.ndarray:
         return np.asarray(ev(like.device_params_batch(like.physical_batch(cubes))), dtype=np.float64)
 
+    # periodic parameters, sampler order (src/lensed.c:1254-1259)
+    kw.setdefault("wrap", [bool(getattr(like.pars[like.pmap[i]], "wrap", False)) for i in range(like.ndims)])
     return nested_sample(lb, like.ndims, nlive=nlive, batch=batch, tol=tol, eff=eff, seed=seed, maxiter=maxiter,
                          transform=like.physical, **kw)
 

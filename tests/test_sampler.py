@@ -52,6 +52,32 @@ def test_same_seed_same_run_and_batch_size_independent_answer():
     assert d.nbatches < c.nbatches/50
 
 
+def test_periodic_dimension_wraps_around():
+    """`wrap` (src/lensed.c:1254-1259, MultiNest's pWrap): a posterior that
+    straddles the 0 / 1 seam of a periodic parameter -- a position angle near
+    0 = 180 degrees -- has Z = 1 counting both sides of the seam.  With wrap the
+    circle is cut opposite the live points, so that one small ellipsoid bounds
+    them; without it the bound spans the whole dimension."""
+    sig = np.array([0.02, 0.03])
+
+    def lb(u):
+        u = np.atleast_2d(u)
+        d0 = np.minimum(u[:, 0], 1.0 - u[:, 0])                  # circular distance from the seam
+        return -0.5*((d0/sig[0])**2 + ((u[:, 1] - 0.5)/sig[1])**2) - np.log(sig*math.sqrt(2*math.pi)).sum()
+    for method in ("reject", "rwalk"):
+        w = S.nested_sample(lb, 2, nlive=300, batch=64, tol=0.01, seed=21, wrap=[True, False], method=method)
+        assert abs(w.logz) < 4*w.logz_err + 0.05, (method, w.logz, w.logz_err)
+        x = w.samples[w.equal_weights(1), 0]
+        assert 0.3 < np.mean(x < 0.5) < 0.7                        # both sides of the seam are populated
+        assert np.all(np.minimum(x, 1 - x) < 0.15)
+    plain = S.nested_sample(lb, 2, nlive=300, batch=64, tol=0.01, seed=21, method="reject")
+    wrapd = S.nested_sample(lb, 2, nlive=300, batch=64, tol=0.01, seed=21, wrap=[True, False], method="reject")
+    assert abs(plain.logz) < 4*plain.logz_err + 0.05              # still exact without, only slower
+    assert wrapd.efficiency > 3*plain.efficiency, (wrapd.efficiency, plain.efficiency)
+    with pytest.raises(ValueError):
+        S.nested_sample(lb, 2, wrap=[False, False, True])
+
+
 def test_two_modes_are_both_found():
     f1, f2 = _gauss([0.25, 0.3], [0.02, 0.02]), _gauss([0.75, 0.7], [0.02, 0.02])
 
