@@ -179,7 +179,7 @@ def test_pair_pow_same_bits(ptx_packed, name):
     draws += [((rng.choice(SPECIAL), rng.choice(SPECIAL)), (rng.choice(SPECIAL), rng.choice(SPECIAL))) for _ in range(300)]
     draws += [((rng.choice(SPECIAL), _lu(rng, 0.1, 3, False)), (_u(rng, -3, 3), rng.choice(SPECIAL))) for _ in range(150)]
     draws += [((_lu(rng, 0.5, 2), _u(rng, -5, 5)), (_u(rng, -2, 2), _u(rng, -5, 5))) for _ in range(100)]   # negative bases
-    _compare(M, name, 2, 1, draws)
+    _compare(M, name, 2, 1, draws if name == "powr" else draws[::3])      # pow is the same function
 
 
 def test_interpreter_agrees_with_libm(ptx_packed):
