@@ -144,6 +144,10 @@ typedef struct
 #define LCU_FAST_ATANH      32u /* atanh in LENS objects = (ln(1+x) - ln(1-x))/2 on the hardware
                                    log2: absolute error 2e-7 (isothermal ellipsoid deflections) */
 
+#define LCU_SOURCE_ONLY     64u /* assemble the program text and stop: the model answers lcu_model_source /
+                                   npars / words / rays_per_thread only (the reference writes the same text
+                                   before it builds, src/lensed.c:714-735).  Contexts without a device only */
+
 typedef struct
 {
     size_t width, height;       /* image size */

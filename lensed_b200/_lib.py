@@ -92,6 +92,7 @@ LCU_FAST_INTRINSICS = 4
 LCU_NO_PAIR = 8
 LCU_FAST_LENS_INTRINSICS = 16
 LCU_FAST_ATANH = 32
+LCU_SOURCE_ONLY = 64
 
 
 def _load():

@@ -942,6 +942,17 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     };
 
     m->source = assemble(0);
+    if(desc->flags & LCU_SOURCE_ONLY)
+    {
+        if(ctx->device >= 0)
+        {
+            set_error("lcu_model_create: LCU_SOURCE_ONLY needs a context without a device");
+            delete m;
+            return LCU_E_ARG;
+        }
+        *out = m;
+        return LCU_OK;
+    }
     if(!ctx->compile(m->source, m->flags, &m->cubin, &m->log))
     {
         set_error("failed to build program\n%s", m->log.c_str());

@@ -61,6 +61,22 @@ def test_compile_only_context_refuses_compute(compile_ctx):
         compile_ctx.fp32_peak_tflops()
 
 
+def test_source_only_model(compile_ctx):
+    """LCU_SOURCE_ONLY: the program text without building it (what the reference
+    writes as <root>kernel.cl before its build, src/lensed.c:714-735)."""
+    img = np.zeros((16, 16), np.float32)
+    full = L.Model(compile_ctx, ["sie", "sersic"], img, img)
+    text = L.Model(compile_ctx, ["sie", "sersic"], img, img, flags=L.LCU_SOURCE_ONLY)
+    assert text.source == full.source and "lcu_compute2" in text.source
+    assert (text.npars, text.words, text.rays_per_thread) == (full.npars, full.words, full.rays_per_thread)
+    assert len(text.cubin) == 0
+    with pytest.raises(L.LensedCudaError):
+        text.kernel_usage("lcu_render_pair")
+    with pytest.raises(L.LensedCudaError) as e:
+        text.loglike(np.zeros(12))
+    assert e.value.code == 5
+
+
 def test_error_reporting(compile_ctx, tmp_path):
     img = np.zeros((8, 8), np.float32)
     with pytest.raises(L.LensedCudaError) as e:
