@@ -28,6 +28,11 @@ __device__ __forceinline__ float hi(u64 a){ float x, y; asm("mov.b64 {%0,%1}, %2
 //      12: FMUL2 x8 + scalar FFMA x8  13: scalar FFMA x8   14: scalar FMUL x8
 //      15: MUFU.EX2 x8   16: MUFU.RCP x8   17: MUFU.EX2 x8 + 16 ALU   18: MUFU.EX2 x8 + scalar FFMA x16
 //      19: MUFU.EX2 x8 + FFMA2 x8   20: MUFU.EX2 x4 + MUFU.LG2 x4
+//      21: FFMA2 x8, three distinct vector-register operands   22: FFMA2 x8, two distinct + one uniform
+//      23: FMUL2 x8, two distinct vector-register operands     24: FADD2 x8, two distinct
+//      25: scalar FFMA x16, three distinct vector-register operands
+//      (modes 1, 8, 9 have one vector-register operand and uniform ones: the difference is what operand
+//       fetch costs -- the render loop's packed instructions mostly have two or three vector operands)
 // (the packed multiply is issued without .ftz: ptxas 12.9 contracts mul.ftz.f32x2 + add.ftz.f32x2 into FFMA2)
 template<int MODE> __global__ void __launch_bounds__(256) kern(float* out, float s, float t)
 {
@@ -67,6 +72,27 @@ template<int MODE> __global__ void __launch_bounds__(256) kern(float* out, float
         if(MODE == 2) {
 #pragma unroll
             for(int i = 0; i < 2*N; ++i) a[i] = add1(mul1(a[i], s), t);
+        }
+        // operands from other chains: values stay bounded (|x| <= 1 keeps products and sums tame enough for timing)
+        if(MODE == 21) {
+#pragma unroll
+            for(int i = 0; i < N; ++i) p[i] = fma2(p[i], p[(i + 3) % N], p[(i + 5) % N]);
+        }
+        if(MODE == 22) {
+#pragma unroll
+            for(int i = 0; i < N; ++i) p[i] = fma2(p[i], p[(i + 3) % N], tt);
+        }
+        if(MODE == 23) {
+#pragma unroll
+            for(int i = 0; i < N; ++i) p[i] = mul2(p[i], p[(i + 3) % N]);
+        }
+        if(MODE == 24) {
+#pragma unroll
+            for(int i = 0; i < N; ++i) p[i] = add2(p[i], p[(i + 3) % N]);
+        }
+        if(MODE == 25) {
+#pragma unroll
+            for(int i = 0; i < 2*N; ++i) a[i] = fma1(a[i], a[(i + 5) % (2*N)], a[(i + 11) % (2*N)]);
         }
         if(MODE == 3) {
 #pragma unroll
@@ -152,6 +178,11 @@ int main()
     run<10>("FFMA2 x8 + scalar FFMA x8", out, 24, 0);
     run<11>("FFMA2 x8 + scalar FMUL x8", out, 24, 0);
     run<12>("FMUL2 x8 + scalar FFMA x8", out, 24, 0);
+    run<21>("FFMA2 x8, 3 vector operands", out, 16, 0);
+    run<22>("FFMA2 x8, 2 vector + 1 uniform", out, 16, 0);
+    run<23>("FMUL2 x8, 2 vector operands", out, 16, 0);
+    run<24>("FADD2 x8, 2 vector operands", out, 16, 0);
+    run<25>("scalar FFMA x16, 3 vector ops", out, 16, 0);
     run<0>("scalar FFMA x16 (again)", out, 16, 0);
     run<15>("MUFU.EX2 x8", out, 0, 8);
     run<16>("MUFU.RCP x8", out, 0, 8);
