@@ -1,4 +1,5 @@
-"""A small PTX interpreter for straight-line float32 device functions.
+"""A small PTX interpreter for the arithmetic device code of this repository
+(float32 ray functions, float64 setters; no threads, no shared memory).
 
 Test infrastructure (CPU only): it lets `tests/test_pair_math.py` run the PTX
 that NVRTC emits for shim.cuh's pair functions (`lcu_pf`: the same quantity for
@@ -77,6 +78,76 @@ def to_frac(b: int) -> Fraction:
     if e == 0:
         return Fraction(s * m, 1 << 149)
     return s * Fraction((1 << 23) | m) * Fraction(2) ** (e - 150)
+
+
+def round_frac64(x: Fraction, mode: str = "rn", neg_zero: bool = False) -> int:
+    """exact rational -> binary64 bits (round to nearest even; other modes as binary32's)"""
+    if x == 0:
+        return (1 << 63) if neg_zero else 0
+    sign = (1 << 63) if x < 0 else 0
+    a = -x if x < 0 else x
+    e = a.numerator.bit_length() - a.denominator.bit_length()
+    if Fraction(2) ** e > a:
+        e -= 1
+    elif Fraction(2) ** (e + 1) <= a:
+        e += 1
+    q = max(e, -1022) - 52
+    scaled = a / (Fraction(2) ** q)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    up = False
+    if rem != 0:
+        if mode == "rn":
+            up = rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (n & 1))
+        elif mode == "rm":
+            up = bool(sign)
+        elif mode == "rp":
+            up = not sign
+    if up:
+        n += 1
+    if n >= (1 << 53):
+        n >>= 1
+        q += 1
+    if n < (1 << 52):
+        return sign | n
+    ebits = q + 52 + 1023
+    if ebits >= 2047:
+        return sign | (0x7FF << 52)
+    return sign | (ebits << 52) | (n & ((1 << 52) - 1))
+
+
+def to_frac64(b: int) -> Fraction:
+    s = -1 if b >> 63 else 1
+    e = (b >> 52) & 0x7FF
+    m = b & ((1 << 52) - 1)
+    if e == 0:
+        return Fraction(s * m, 1 << 1074)
+    return s * Fraction((1 << 52) | m) * Fraction(2) ** (e - 1075)
+
+
+def is_nan64(b: int) -> bool:
+    return (b >> 52) & 0x7FF == 0x7FF and (b & ((1 << 52) - 1)) != 0
+
+
+def is_inf64(b: int) -> bool:
+    return (b & ~(1 << 63)) == (0x7FF << 52)
+
+
+def fma64(a: int, b: int, c: int) -> int:
+    """fma.rn.f64 on bit patterns: exact product and sum, one rounding"""
+    if is_nan64(a) or is_nan64(b) or is_nan64(c) or is_inf64(a) or is_inf64(b) or is_inf64(c):
+        x, y, z = b2d(a), b2d(b), b2d(c)
+        try:
+            return d2b(x*y + z)                    # IEEE special values: the unfused expression gives the same
+        except OverflowError:
+            return d2b(float("nan"))
+    p = to_frac64(a) * to_frac64(b)
+    r = p + to_frac64(c)
+    nz = False
+    if r == 0:
+        ps = (a ^ b) >> 63
+        nz = bool(ps and (c >> 63)) if p == 0 and (c & ~(1 << 63)) == 0 else False
+    return round_frac64(r, "rn", nz)
 
 
 def round_frac(x: Fraction, mode: str = "rn", flush: bool = False, neg_zero: bool = False) -> int:
@@ -315,12 +386,27 @@ class Function:
         self.name, self.params, self.body = name, params, body
         self.labels = {}
         self.insns = []
+        pending = ""
         for line in body:
             m = re.match(r"^(\$?[\w$]+):$", line)
-            if m:
+            if m and not pending:
                 self.labels[m.group(1)] = len(self.insns)
-            else:
-                self.insns.append(line)
+                continue
+            # a statement runs to its ';' (call statements span several lines)
+            pending = (pending + " " + line).strip()
+            if pending.endswith(";"):
+                self.insns.append(pending)
+                pending = ""
+
+
+def _body_lines(text: str):
+    out = []
+    for raw in text.split("\n"):
+        line = raw.strip()
+        if not line or line in ("{", "}") or line.startswith((".reg", ".pragma", ".loc", ".local", ".param")):
+            continue
+        out.append(line)
+    return out
 
 
 class Module:
@@ -335,16 +421,18 @@ class Module:
             data = bytes(int(v) for v in m.group(3).split(","))
             self.globals[m.group(1)] = (self._next_global, data)
             self._next_global += (len(data) + 255) & ~255
+        for m in re.finditer(r"\.global\s+\.align\s+\d+\s+\.(?:u32|b32|s32|f32)\s+(\w+)\s*=\s*(-?\w+);", text):
+            v = m.group(2)
+            word = int(v[2:], 16) if v[:2] in ("0f", "0F") else int(v, 0)
+            self.globals[m.group(1)] = (self._next_global, (word & M32).to_bytes(4, "little"))
+            self._next_global += 256
         for m in re.finditer(r"\.visible\s+\.entry\s+(\w+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
             params = re.findall(r"(\w+_param_\d+)", m.group(2))
-            body = []
-            for raw in m.group(3).split("\n"):
-                line = raw.strip()
-                if not line or line.startswith(".reg") or line.startswith(".pragma") or line.startswith(".loc") \
-                        or line.startswith(".local"):
-                    continue
-                body.append(line)
-            self.functions[m.group(1)] = Function(m.group(1), params, body)
+            self.functions[m.group(1)] = Function(m.group(1), params, _body_lines(m.group(3)))
+        # device functions that NVRTC did not inline (libdevice slow paths): name(params) { body }
+        for m in re.finditer(r"\.func\s*(?:\([^)]*\))?\s*(\w+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
+            params = re.findall(r"(\w+_param_\d+)", m.group(2))
+            self.functions[m.group(1)] = Function(m.group(1), params, _body_lines(m.group(3)))
 
     def run(self, name: str, inputs, n_out: int, max_steps: int = 20000):
         """run entry `name(float* out, const float* in0, const float* in1, ...)`;
@@ -368,10 +456,13 @@ class Module:
 
 
 class _Machine:
-    def __init__(self, module, fn, params, mem):
+    def __init__(self, module, fn, params, mem, depth: int = 0):
         self.module, self.fn, self.params, self.mem = module, fn, params, mem
         self.reg = {}
-        self.local_base = 0x20000000
+        self.depth = depth
+        self.local_base = 0x20000000 + depth*0x100000
+        self.pspace = {}                           # .param variables of call sequences: name -> {offset: value}
+        self.retvals = {}                          # func_retval0 of this function: offset -> value
 
     # operand access -------------------------------------------------------
     def val(self, tok: str, width: int = 32) -> int:
@@ -438,10 +529,36 @@ class _Machine:
         mode = next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn")
         typ = mods[-1] if mods else ""
 
-        if name == "ld":
-            if mods[0] == "param":
-                R[args[0]] = self.params[re.match(r"^\[(\w+)\]$", args[1]).group(1)]
+        if name == "call":
+            m = re.match(r"^(?:\((\w+)\)\s*,)?\s*(\w+)\s*,\s*\(([^)]*)\)$", rest)
+            if not m or m.group(2) not in self.module.functions:
+                raise NotImplementedError(line)
+            callee = self.module.functions[m.group(2)]
+            actual = [a.strip() for a in m.group(3).split(",") if a.strip()]
+            sub = _Machine(self.module, callee, {p: self.pspace[a] for p, a in zip(callee.params, actual)}, self.mem,
+                           self.depth + 1)
+            sub.execute(200000)
+            if m.group(1):
+                self.pspace[m.group(1)] = sub.retvals
+            return
+        if name in ("ld", "st") and mods[0] == "param":
+            tok = args[1] if name == "ld" else args[0]
+            m = re.match(r"^\[(\w+)(?:\+(\d+))?\]$", tok)
+            var, off = m.group(1), int(m.group(2) or 0)
+            wide = typ in ("u64", "b64", "s64", "f64")
+            if name == "st":
+                space = self.retvals if var.startswith("func_retval") else self.pspace.setdefault(var, {})
+                space[off] = self.val(args[1], 64) & (M64 if wide else M32)
                 return
+            src = self.params[var] if var in self.params else self.pspace[var]
+            R[args[0]] = src[off] if isinstance(src, dict) else src
+            return
+        if name == "st" and args[1].startswith("{"):          # st.global.v2 / .v4 (32-bit elements)
+            a = self.addr(args[0])
+            for i, t in enumerate(x.strip() for x in args[1].strip("{}").split(",")):
+                self.mem[a + 4*i] = self.val(t) & M32
+            return
+        if name == "ld":
             a = self.addr(args[1])
             wide = typ in ("u64", "b64", "s64", "f64")
             word = (lambda at: self.mem.get(at, 0) | (self.mem.get(at + 4, 0) << 32)) if wide else (lambda at: self.mem.get(at, 0))
@@ -453,7 +570,10 @@ class _Machine:
             return
         if name == "st":
             a = self.addr(args[0])
-            self.mem[a] = self.val(args[1], 64) & M32
+            v = self.val(args[1], 64)
+            self.mem[a] = v & M32
+            if typ in ("u64", "b64", "s64", "f64"):
+                self.mem[a + 4] = (v >> 32) & M32
             return
         if name == "cvta":
             R[args[0]] = self.val(args[1], 64)
@@ -483,8 +603,22 @@ class _Machine:
                 out |= _arith(name, (a >> sh) & M32, (b >> sh) & M32, cc, mode, flush) << sh
             R[args[0]] = out
             return
-        if name == "mul" and typ == "f64":
-            R[args[0]] = d2b(b2d(self.val(args[1], 64)) * b2d(self.val(args[2], 64)))
+        if typ == "f64" and name in ("add", "sub", "mul", "div", "fma", "abs", "neg", "rcp", "sqrt", "min", "max"):
+            R[args[0]] = self.f64(name, mods, [self.val(a, 64) for a in args[1:]])
+            return
+        if name == "setp" and typ == "f64":
+            x, y = b2d(self.val(args[1], 64)), b2d(self.val(args[2], 64))
+            nan = x != x or y != y
+            cmp = mods[0]
+            if cmp in ("num", "nan"):
+                R[args[0]] = nan == (cmp == "nan")
+            elif nan:
+                R[args[0]] = cmp in ("equ", "neu", "ltu", "leu", "gtu", "geu")
+            else:
+                R[args[0]] = {"eq": x == y, "ne": x != y, "lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y}[cmp[:2]]
+            return
+        if name == "abs" and typ == "s32":
+            R[args[0]] = abs(_s32(self.val(args[1]))) & M32
             return
         if name in ("abs", "neg") and typ == "f32":
             v = self.val(args[1])
@@ -610,8 +744,69 @@ class _Machine:
             return
         raise NotImplementedError(line)
 
+    @staticmethod
+    def f64(name, mods, a):
+        """binary64 arithmetic (rn) on bit patterns"""
+        if name == "abs":
+            return a[0] & ~(1 << 63)
+        if name == "neg":
+            return a[0] ^ (1 << 63)
+        if name == "fma":
+            return fma64(a[0], a[1], a[2])
+        x = b2d(a[0])
+        y = b2d(a[1]) if len(a) > 1 else None
+        if name == "rcp":
+            if "approx" in mods:
+                # fast gross approximation: the low 32 bits of the argument are ignored, those of the result zero
+                x = b2d(a[0] & ~M32)
+                if x == 0 or x != x or math.isinf(x):
+                    return d2b(math.copysign(math.inf, x)) if x == 0 else (d2b(math.copysign(0.0, x)) if math.isinf(x) else a[0])
+                return d2b(1.0/x) & ~M32
+            x, y = 1.0, x
+            name = "div"
+        try:
+            if name == "add":
+                return d2b(x + y)
+            if name == "sub":
+                return d2b(x - y)
+            if name == "mul":
+                return d2b(x * y)
+            if name == "sqrt":
+                return d2b(math.sqrt(x)) if x >= 0 else d2b(math.nan)
+            if name in ("min", "max"):
+                if x != x or y != y:
+                    return a[1] if x != x else a[0]
+                return d2b(min(x, y) if name == "min" else max(x, y))
+            if name == "div":
+                if y == 0.0:
+                    if x == 0.0 or x != x:
+                        return d2b(math.nan)
+                    return d2b(math.copysign(math.inf, x)*math.copysign(1.0, y))
+                return d2b(x / y)
+        except OverflowError:
+            return d2b(math.inf if (x > 0) == (y is None or y > 0) else -math.inf)
+        raise NotImplementedError(name)
+
     def cvt(self, mods, v: int) -> int:
         dst, src = mods[-2], mods[-1]
+        if src == "f64" and dst in ("f64", "s32", "s64", "u32", "u64"):
+            x = b2d(v)
+            im = next((m for m in mods if m in ("rni", "rzi", "rmi", "rpi")), None)
+            if dst == "f64":
+                if x != x or math.isinf(x) or im is None:
+                    return v
+                n = _round_int(Fraction(x), im)
+                return d2b(math.copysign(float(n), x))
+            if x != x:
+                return 0
+            bits = 64 if dst.endswith("64") else 32
+            lo, hi = ((-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if dst[0] == "s" else (0, (1 << bits) - 1))
+            n = (lo if x < 0 else hi) if math.isinf(x) else max(lo, min(hi, _round_int(Fraction(x), im or "rzi")))
+            return n & ((1 << bits) - 1)
+        if dst == "f64" and src in ("s32", "u32", "u64"):
+            return d2b(float(_s32(v) if src == "s32" else (v & M32 if src == "u32" else v & M64)))
+        if src == "u64" and dst == "u32":
+            return v & M32
         flush = "ftz" in mods
         sat = "sat" in mods
         imode = next((m for m in mods if m in ("rni", "rzi", "rmi", "rpi")), None)
