@@ -1,0 +1,153 @@
+"""The CUDA kernels themselves, run on the CPU.
+
+`tools/ptx_emu.py` executes NVRTC's PTX of a model's program as a grid of
+thread blocks (threads as coroutines that meet at `bar.sync` and, per warp, at
+`shfl.sync`; global, constant, shared and parameter memory; exact IEEE
+arithmetic).  That is enough to run the whole evaluation of a small image --
+`lcu_set_params`' body, `lcu_render_pair`, `lcu_render_s1`, `lcu_convolve` /
+`lcu_convolve_small` with the fused chi^2, `lcu_reduce` -- and hold the result
+against the oracle exactly as the GPU parity tests do: model image per pixel,
+log-likelihood, pair kernel = one-ray kernel bit for bit, both convolution
+kernels bit for bit.  What it does not exercise is the hardware (the special-
+function unit is a correctly rounded stand-in) and ptxas; for those see
+tests/test_gpu_parity.py and test_pair_rays.py.  Sizes are tiny: the
+interpreter runs ~10^5 instructions per second.
+"""
+import dataclasses
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+import ptx_emu as E  # noqa: E402
+import helpers as H  # noqa: E402
+import test_pair_rays as R  # noqa: E402
+
+pytest.importorskip("cuda.bindings.nvrtc")
+
+IMG, WGT, RAW, MODEL, PART, LNEW, RAW1, PART1, MODEL1 = (0x100000*k for k in range(1, 10))
+OUT_VALUE, OUT_CHI2 = 1, 4
+
+
+def _put(mem, addr, arr):
+    for i, v in enumerate(np.ascontiguousarray(arr).view(np.uint32).ravel()):
+        mem[addr + 4*i] = int(v)
+
+
+def _get(mem, addr, shape, dtype=np.float32):
+    n = int(np.prod(shape))*np.dtype(dtype).itemsize//4
+    return np.array([mem.get(addr + 4*i, 0) for i in range(n)], np.uint32).view(dtype).reshape(shape)
+
+
+def _render_args(cfg, pcs, nk, value, partial, ngroups, mode):
+    # lcu_render_args of kernel/lensed.cu: pcs, k0, nk, objs, value, error, image, weight, chimap, partial, ngroups, mode, tail
+    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, 0, nk, 0, value, 0, IMG, WGT, 0, partial, ngroups, mode, 0, 0, 0.0)
+    return a + b"\0"*(128 - len(a))
+
+
+def _convolve_args(raw, model, partial, rows, ngroups, gpr, mode):
+    # lcu_convolve_args: raw, model, image, weight, chimap, partial, row0, row1, ngroups, gpr, mode, tail
+    a = struct.pack("<QQQQQQiiiii", raw, model, IMG, WGT, 0, partial, 0, rows, ngroups, gpr, mode)
+    a += b"\0"*(72 - len(a)) + struct.pack("<QQd", 0, 0, 0.0)
+    return a
+
+
+def _scene(psf):
+    """a 20 x 12 scene with the lens and the source inside the frame"""
+    import lensed_b200 as L
+    base = H.golden_config("sie")                                    # sie + sersic
+    h, w = 12, 20
+    params = base.params.copy()
+    params[:5] = [10.3, 6.2, 3.0, 0.8, 30.0]                         # lens x y r q pa
+    params[5:12] = [11.0, 6.6, 1.5, -3.0, 1.5, 0.7, 100.0]           # source x y r mag n q pa
+    cfg = dataclasses.replace(base, name="tiny-sie" + ("-psf" if psf is not None else ""), params=params,
+                              image=np.zeros((h, w), np.float32), weight=np.ones((h, w), np.float32), rule="sub2", psf=psf)
+    _, model, _ = cfg.oracle().loglike(params, want_maps=True)
+    cfg.image, cfg.weight = H.workloads.observe(model, 5)
+    cfg.weight[3, 4] = 0                                             # a masked pixel
+    return cfg, L
+
+
+def _program(cfg, L):
+    ctx = L.Context(device=-1)
+    try:
+        m = cfg.product(ctx, flags=L.LCU_SOURCE_ONLY)
+        text, words, pcs = m.source, m.words, None
+    finally:
+        ctx.close()
+    return E.Module(R._compile_ptx(text, 0)), text, words
+
+
+def _object_block(M, text, cfg, words):
+    """lcu_set_params' body, interpreted (tests/test_pair_rays.py::test_set_params_against_oracle checks it)"""
+    head = text.partition("// kernel/lensed.cu\n")[0]
+    S = E.Module(R._compile_ptx(head + R.SETTER, 0))
+    out = S.run("k_set", [[E.f2b(float(v)) for v in cfg.params]], words, max_steps=2000000)
+    return [v or 0 for v in out]
+
+
+def test_render_and_reduce_without_psf():
+    from lensed_b200 import api
+    cfg, L = _scene(None)
+    M, text, words = _program(cfg, L)
+    block = _object_block(M, text, cfg, words)
+    h, w = cfg.image.shape
+    npix, ngroups = h*w, (h*w + 31)//32
+    qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
+    consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW, PART, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_reduce", (1,), 256, [ngroups, PART, E.d2b(-0.5), LNEW], mem)
+    M.launch("lcu_render_s1", ((npix + 255)//256, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW1, PART1, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    om = cfg.oracle()
+    ref_l, ref_model, _ = om.loglike(cfg.params, want_maps=True)
+    got = _get(mem, RAW, (h, w))
+    rel = H.rel_err(got, ref_model)
+    assert rel.max() <= 1e-5, rel.max()                              # BASELINE.json: per-pixel relative error
+    lnew = float(_get(mem, LNEW, (1,), np.float64)[0])
+    assert abs(lnew - ref_l) <= 1e-6*abs(ref_l), (lnew, ref_l)       # BASELINE.json: log-likelihood
+    # two rays per thread: the one-ray kernel's bits, values and chi^2 partial sums
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
+
+
+def test_render_convolve_reduce_with_psf():
+    from lensed_b200 import api
+    psf = H.workloads.gaussian_psf(5, 3, 1.0)                        # 5 wide, 3 high
+    cfg, L = _scene(psf)
+    M, text, words = _program(cfg, L)
+    block = _object_block(M, text, cfg, words)
+    h, w = cfg.image.shape
+    npix, gpr = h*w, (w + 31)//32
+    ngroups = h*gpr
+    qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
+    consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block,
+              "lcu_psf": psf.astype(np.float32).view(np.uint32).ravel()}
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW, 0, (npix + 31)//32, OUT_VALUE)], mem, consts)
+    M.launch("lcu_convolve", ((w + 63)//64, (h + 31)//32, 1), 256,
+             [_convolve_args(RAW, MODEL, PART, h, ngroups, gpr, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_reduce", (1,), 256, [ngroups, PART, E.d2b(-0.5), LNEW], mem)
+    M.launch("lcu_convolve_small", ((w + 31)//32, (h + 7)//8, 1), 256,
+             [_convolve_args(RAW, MODEL1, PART1, h, ngroups, gpr, OUT_VALUE | OUT_CHI2)], mem, consts)
+    om = cfg.oracle()
+    ref_l, ref_model, _ = om.loglike(cfg.params, want_maps=True)
+    raw = _get(mem, RAW, (h, w))
+    # the convolution is the reference's arithmetic in the reference's order: bit-exact given the same input
+    assert np.array_equal(_get(mem, MODEL, (h, w)).view(np.uint32), np.asarray(om.convolve(raw), np.float32).view(np.uint32))
+    assert H.rel_err(_get(mem, MODEL, (h, w)), ref_model).max() <= 1e-5
+    lnew = float(_get(mem, LNEW, (1,), np.float64)[0])
+    assert abs(lnew - ref_l) <= 1e-6*abs(ref_l), (lnew, ref_l)
+    # the small-launch convolution kernel: same bits, image and partial sums
+    assert np.array_equal(_get(mem, MODEL, (npix,)).view(np.uint32), _get(mem, MODEL1, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))

@@ -1,5 +1,6 @@
-"""A small PTX interpreter for the arithmetic device code of this repository
-(float32 ray functions, float64 setters; no threads, no shared memory).
+"""A small PTX interpreter for the device code of this repository: float32 ray
+functions, float64 setters, and whole kernels as grids of thread blocks
+(Module.launch: bar.sync, shfl.sync, shared / constant / parameter memory).
 
 Test infrastructure (CPU only): it lets `tests/test_pair_math.py` run the PTX
 that NVRTC emits for shim.cuh's pair functions (`lcu_pf`: the same quantity for
@@ -403,7 +404,7 @@ def _body_lines(text: str):
     out = []
     for raw in text.split("\n"):
         line = raw.strip()
-        if not line or line in ("{", "}") or line.startswith((".reg", ".pragma", ".loc", ".local", ".param")):
+        if not line or line in ("{", "}") or line.startswith((".reg", ".pragma", ".loc", ".local", ".param", ".shared")):
             continue
         out.append(line)
     return out
@@ -426,7 +427,19 @@ class Module:
             word = int(v[2:], 16) if v[:2] in ("0f", "0F") else int(v, 0)
             self.globals[m.group(1)] = (self._next_global, (word & M32).to_bytes(4, "little"))
             self._next_global += 256
-        for m in re.finditer(r"\.visible\s+\.entry\s+(\w+)\s*\(([^)]*)\)\s*\{(.*?)\n\}", text, re.S):
+        # uninitialised __constant__ arrays (filled by the caller of launch()) and __shared__ variables
+        self.consts, self.shared = {}, {}
+        self.struct_params = set()
+        for m in re.finditer(r"\.const\s+\.align\s+\d+\s+\.b8\s+(\w+)\[(\d+)\];", text):
+            self.consts[m.group(1)] = (self._next_global, int(m.group(2)))
+            self._next_global += (int(m.group(2)) + 255) & ~255
+        off = 0
+        for m in re.finditer(r"\.shared\s+\.align\s+(\d+)\s+\.\w+\s+(\w+)(?:\[(\d+)\])?;", text):
+            al = int(m.group(1))
+            off = (off + al - 1)//al*al
+            self.shared[m.group(2)] = 0x30000000 + off
+            off += int(m.group(3) or 8)
+        for m in re.finditer(r"\.visible\s+\.entry\s+(\w+)\s*\(([^)]*)\)\s*(?:\.\w+[^\n{]*\n\s*)*\{(.*?)\n\}", text, re.S):
             params = re.findall(r"(\w+_param_\d+)", m.group(2))
             self.functions[m.group(1)] = Function(m.group(1), params, _body_lines(m.group(3)))
         # device functions that NVRTC did not inline (libdevice slow paths): name(params) { body }
@@ -455,7 +468,101 @@ class Module:
         return [mem.get(out_addr + 4 * i) for i in range(n_out)]
 
 
+    def launch(self, name: str, grid, block, params, mem, consts=None, max_steps: int = 5_000_000):
+        """Run kernel `name` over a grid (x, y, z) of blocks of `block` threads.
+        params: one entry per kernel parameter -- an int for a scalar, bytes for a
+        struct passed by value.  mem: the address -> 32-bit word dictionary shared
+        by all threads (global memory; the caller places its buffers in it).
+        consts: __constant__ arrays by name (lists of 32-bit words).  Threads of a
+        block run as coroutines that meet at bar.sync and, per warp, at shfl.sync:
+        enough for kernels whose warps are converged at those points."""
+        fn = self.functions[name]
+        for addr, data in self.globals.values():
+            for i in range(0, len(data), 4):
+                mem.setdefault(addr + i, int.from_bytes(data[i:i + 4], "little"))
+        for cname, words in (consts or {}).items():
+            base, size = self.consts[cname]
+            assert 4*len(words) <= size, cname
+            for i, w in enumerate(words):
+                mem[base + 4*i] = int(w) & M32
+        env = {}
+        for i, (pname, value) in enumerate(zip(fn.params, params)):
+            if isinstance(value, (bytes, bytearray)):          # struct by value: lives in param space, addressable
+                env[pname] = 0x40000000 + 0x1000*i
+                self.struct_params.add(pname)
+                for k in range(0, len(value), 4):
+                    mem[env[pname] + k] = int.from_bytes(value[k:k + 4], "little")
+            else:
+                env[pname] = value
+        gx, gy, gz = (tuple(grid) + (1, 1, 1))[:3]
+        for bz in range(gz):
+            for by in range(gy):
+                for bx in range(gx):
+                    for a in [k for k in mem if 0x30000000 <= k < 0x30100000]:
+                        del mem[a]                 # shared memory does not outlive the block
+                    self._run_block(fn, env, mem, (bx, by, bz), (gx, gy, gz), block, max_steps)
+
+    def _run_block(self, fn, env, mem, bid, gdim, nthreads, max_steps):
+        threads = []
+        for t in range(nthreads):
+            mach = _Machine(self, fn, env, mem)
+            mach.special = {"%tid.x": t, "%tid.y": 0, "%tid.z": 0, "%ntid.x": nthreads, "%ntid.y": 1, "%ntid.z": 1,
+                            "%ctaid.x": bid[0], "%ctaid.y": bid[1], "%ctaid.z": bid[2],
+                            "%nctaid.x": gdim[0], "%nctaid.y": gdim[1], "%nctaid.z": gdim[2],
+                            "%laneid": t % 32, "%warpid": t//32}
+            mach.local_base = 0x20000000 + t*0x10000
+            threads.append(mach.steps(max_steps))
+        waiting = {}                               # thread -> event it stopped at
+        alive = set(range(nthreads))
+        reply = {t: None for t in alive}
+        while alive:
+            for t in sorted(alive - set(waiting)):
+                try:
+                    waiting[t] = threads[t].send(reply[t])
+                    reply[t] = None
+                except StopIteration:
+                    alive.discard(t)
+            if not alive:
+                break
+            progressed = False
+            # shuffles: all live threads of a warp stand at one
+            for w in range((nthreads + 31)//32):
+                lanes = [t for t in range(32*w, min(32*w + 32, nthreads)) if t in alive]
+                if lanes and all(t in waiting and waiting[t][0] == "shfl" for t in lanes):
+                    vals = {t % 32: waiting[t][2] for t in lanes}
+                    for t in lanes:
+                        _, mode, v, b, c = waiting[t]
+                        lane = t % 32
+                        seg, cval = (c >> 8) & 31, c & 31
+                        top = (lane & seg) | (cval & ~seg & 31)
+                        if mode == "down":
+                            src = lane + b
+                            ok = src <= top
+                        elif mode == "up":
+                            src = lane - b
+                            ok = src >= (lane & seg)
+                        elif mode == "bfly":
+                            src = lane ^ b
+                            ok = src <= top
+                        else:                      # idx
+                            src = (lane & seg) | (b & ~seg & 31)
+                            ok = src <= top
+                        ok = ok and src in vals     # a lane that has exited supplies nothing
+                        reply[t] = (vals[src] if ok else v, ok)
+                        del waiting[t]
+                    progressed = True
+            if alive and all(t in waiting and waiting[t][0] == "bar" for t in alive):
+                for t in alive:
+                    reply[t] = None
+                waiting.clear()
+                progressed = True
+            if not progressed and all(t in waiting for t in alive):
+                raise RuntimeError("deadlock in %s: threads wait at %s" % (fn.name, {e[0] for e in waiting.values()}))
+
+
 class _Machine:
+    special = {}
+
     def __init__(self, module, fn, params, mem, depth: int = 0):
         self.module, self.fn, self.params, self.mem = module, fn, params, mem
         self.reg = {}
@@ -468,13 +575,21 @@ class _Machine:
     def val(self, tok: str, width: int = 32) -> int:
         tok = tok.strip()
         if tok.startswith("%"):
-            return self.reg[tok]
+            if tok in self.reg:
+                return self.reg[tok]
+            return self.special[tok]
         if tok.startswith("0f") or tok.startswith("0F"):
             return int(tok[2:], 16)
         if tok.startswith("0d") or tok.startswith("0D"):
             return int(tok[2:], 16)
         if tok in self.module.globals:
             return self.module.globals[tok][0]
+        if tok in self.module.consts:
+            return self.module.consts[tok][0]
+        if tok in self.params and isinstance(self.params[tok], int):
+            return self.params[tok]
+        if tok in self.module.shared:
+            return self.module.shared[tok]
         if tok.startswith("__local_depot"):
             return self.local_base
         if re.match(r"^-?(0x[0-9a-fA-F]+|\d+)$", tok):
@@ -497,6 +612,12 @@ class _Machine:
 
     # execution ------------------------------------------------------------
     def execute(self, max_steps: int):
+        """single thread: no collectives"""
+        for event in self.steps(max_steps):
+            raise NotImplementedError("%s outside launch()" % event[0])
+
+    def steps(self, max_steps: int):
+        """run until the end; yields at bar.sync and shfl.sync (see Module.launch)"""
         pc, steps = 0, 0
         insns = self.fn.insns
         while pc < len(insns):
@@ -510,12 +631,23 @@ class _Machine:
                 if not self.pred(guard.group(1)):
                     continue
                 line = guard.group(2)
-            op, _, rest = line.partition(" ")
+            op, rest = (re.split(r"\s+", line, maxsplit=1) + [""])[:2]
             rest = rest.strip()
             if op in ("ret", "exit"):
                 return
             if op in ("bra", "bra.uni"):
                 pc = self.fn.labels[rest]
+                continue
+            if op.startswith("bar.") or op.startswith("barrier."):
+                yield ("bar",)
+                continue
+            if op.startswith("shfl.sync"):
+                args = [a.strip() for a in rest.split(",")]
+                dst, _, pdst = args[0].partition("|")
+                value, ok = yield ("shfl", op.split(".")[2], self.val(args[1]), self.val(args[2]), self.val(args[3]))
+                self.reg[dst] = value
+                if pdst:
+                    self.reg[pdst] = ok
                 continue
             self.step(op, rest, line)
 
@@ -543,9 +675,16 @@ class _Machine:
             return
         if name in ("ld", "st") and mods[0] == "param":
             tok = args[1] if name == "ld" else args[0]
-            m = re.match(r"^\[(\w+)(?:\+(\d+))?\]$", tok)
+            m = re.match(r"^\[(%?\w+)(?:\+(\d+))?\]$", tok)
             var, off = m.group(1), int(m.group(2) or 0)
             wide = typ in ("u64", "b64", "s64", "f64")
+            if name == "ld" and (var.startswith("%") or var in self.module.struct_params):
+                base = (self.val(var, 64) if var.startswith("%") else self.params[var]) + off
+                size = 8 if wide else 4
+                for i, d in enumerate(t.strip() for t in args[0].strip("{}").split(",")):
+                    a = base + i*size
+                    R[d] = self.mem.get(a, 0) | ((self.mem.get(a + 4, 0) << 32) if wide else 0)
+                return
             if name == "st":
                 space = self.retvals if var.startswith("func_retval") else self.pspace.setdefault(var, {})
                 space[off] = self.val(args[1], 64) & (M64 if wide else M32)
@@ -560,6 +699,9 @@ class _Machine:
             return
         if name == "ld":
             a = self.addr(args[1])
+            if typ in ("u8", "s8", "b8"):
+                R[args[0]] = self.mem.get(a, 0) & 0xFF
+                return
             wide = typ in ("u64", "b64", "s64", "f64")
             word = (lambda at: self.mem.get(at, 0) | (self.mem.get(at + 4, 0) << 32)) if wide else (lambda at: self.mem.get(at, 0))
             if args[0].startswith("{"):            # ld.global.v2 / .v4
@@ -671,7 +813,11 @@ class _Machine:
             else:
                 w = 64 if typ.endswith("64") else 32
                 a, b = self.val(a_tok, w), self.val(b_tok, w)
-                if typ.startswith("s"):
+                if typ.endswith("16"):
+                    a, b = a & 0xFFFF, b & 0xFFFF
+                    if typ.startswith("s"):
+                        a, b = a - ((a >> 15) << 16), b - ((b >> 15) << 16)
+                elif typ.startswith("s"):
                     a, b = (_s64(a), _s64(b)) if w == 64 else (_s32(a), _s32(b))
                 R[args[0]] = {"eq": a == b, "ne": a != b, "lt": a < b, "le": a <= b, "gt": a > b, "ge": a >= b,
                               "lo": a < b, "ls": a <= b, "hi": a > b, "hs": a >= b}[cmp]
@@ -702,6 +848,9 @@ class _Machine:
             n = self.val(args[2]) & M32
             R[args[0]] = (self.val(args[1], w) << n) & (M64 if w == 64 else M32) if n < w else 0
             return
+        if name == "shr" and typ == "u16":
+            R[args[0]] = (self.val(args[1]) & 0xFFFF) >> min(self.val(args[2]) & M32, 16)
+            return
         if name == "shr":
             w = 64 if typ.endswith("64") else 32
             n = min(self.val(args[2]) & M32, w)
@@ -716,10 +865,17 @@ class _Machine:
             v = ((hi << 32) | lo) << n if mods[0] == "l" else ((hi << 32) | lo) >> n
             R[args[0]] = ((v >> 32) & M32) if mods[0] == "l" else (v & M32)
             return
-        if name in ("add", "sub") and typ in ("s32", "u32", "s64", "u64"):
-            w = 64 if typ.endswith("64") else 32
+        if name in ("add", "sub") and typ in ("s16", "u16", "s32", "u32", "s64", "u64"):
+            w = int(typ[1:])
             a, b = self.val(args[1], w), self.val(args[2], w)
-            R[args[0]] = (a + b if name == "add" else a - b) & (M64 if w == 64 else M32)
+            R[args[0]] = (a + b if name == "add" else a - b) & ((1 << w) - 1)
+            return
+        if name == "atom" and mods[-2] == "add":               # atom.global.add.u32 d, [a], b
+            a = self.addr(args[1])
+            R[args[0]] = self.mem.get(a, 0)
+            self.mem[a] = (R[args[0]] + self.val(args[2])) & M32
+            return
+        if name in ("membar", "fence"):
             return
         if name == "neg" and typ == "s32":
             R[args[0]] = (-self.val(args[1])) & M32
@@ -736,8 +892,23 @@ class _Machine:
                 a, b = _s32(a), _s32(b)
             R[args[0]] = (a * b + self.val(args[3], 64)) & M64
             return
-        if name == "mul" and "lo" in mods:
-            R[args[0]] = (self.val(args[1]) * self.val(args[2])) & M32
+        if name in ("mul", "mad") and ("lo" in mods or "hi" in mods):
+            w = int(typ[1:])
+            mask = (1 << w) - 1
+            sg = (lambda v: (v & mask) - ((v & mask) >> (w - 1) << w)) if typ.startswith("s") else (lambda v: v & mask)
+            prod = sg(self.val(args[1], 64)) * sg(self.val(args[2], 64))
+            r = prod >> w if "hi" in mods else prod
+            if name == "mad":
+                r += sg(self.val(args[3], 64))
+            R[args[0]] = r & mask
+            return
+        if name in ("div", "rem") and typ in ("s32", "u32", "s64", "u64"):
+            w = 64 if typ.endswith("64") else 32
+            sg = (_s64 if w == 64 else _s32) if typ.startswith("s") else (lambda v: v & (M64 if w == 64 else M32))
+            a, b = sg(self.val(args[1], w)), sg(self.val(args[2], w))
+            q = abs(a)//abs(b) if b else 0
+            q = q if (a < 0) == (b < 0) else -q              # truncation, as C
+            R[args[0]] = (q if name == "div" else a - q*b) & (M64 if w == 64 else M32)
             return
         if name == "cvt":
             R[args[0]] = self.cvt(mods, self.val(args[1], 64))
@@ -838,12 +1009,20 @@ class _Machine:
                 return (lo if v & 0x80000000 else hi) & M32
             n = _round_int(to_frac(v), imode)
             return max(lo, min(hi, n)) & M32
-        if src in ("s32", "u32") and dst == "f32":
-            n = _s32(v) if src == "s32" else v & M32
+        if src in ("s32", "u32", "s64", "u64") and dst == "f32":
+            n = _s32(v) if src == "s32" else v & M32 if src == "u32" else _s64(v) if src == "s64" else v & M64
             mode = next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn")
             return round_frac(Fraction(n), mode)
-        if src == "u32" and dst == "u64":
+        if src == "u32" and dst in ("u64", "s64"):
             return v & M32
+        if src == "s32" and dst in ("s64", "u64"):
+            return _s32(v) & M64
+        if src in ("u64", "s64") and dst in ("u32", "s32"):
+            return v & M32
+        if src in ("u16", "u8") and dst in ("u32", "s32", "u64"):
+            return v & (0xFFFF if src == "u16" else 0xFF)
+        if dst in ("u16", "s16") and src in ("u32", "s32", "u64", "s64"):
+            return v & 0xFFFF
         if src == "s32" and dst == "s64":
             return _s32(v) & M64
         if src == "s64" and dst == "f64":
