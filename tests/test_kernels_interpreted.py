@@ -4,8 +4,9 @@
 thread blocks (threads as coroutines that meet at `bar.sync` and, per warp, at
 `shfl.sync`; global, constant, shared and parameter memory; exact IEEE
 arithmetic).  That is enough to run the whole evaluation of a small image --
-`lcu_set_params`' body, `lcu_render_pair`, `lcu_render_s1`, `lcu_convolve` /
-`lcu_convolve_small` with the fused chi^2, `lcu_reduce` -- and hold the result
+`lcu_set_params`' body, `lcu_render_pair[_err]`, `lcu_render_s1`, `lcu_render_s8`
+with the fused final reduction, `lcu_convolve` / `lcu_convolve_small` with the
+fused chi^2, `lcu_reduce` -- and hold the result
 against the oracle exactly as the GPU parity tests do: model image per pixel,
 log-likelihood, pair kernel = one-ray kernel bit for bit, both convolution
 kernels bit for bit.  What it does not exercise is the hardware (the special-
@@ -28,8 +29,8 @@ import test_pair_rays as R  # noqa: E402
 
 pytest.importorskip("cuda.bindings.nvrtc")
 
-IMG, WGT, RAW, MODEL, PART, LNEW, RAW1, PART1, MODEL1 = (0x100000*k for k in range(1, 10))
-OUT_VALUE, OUT_CHI2 = 1, 4
+IMG, WGT, RAW, MODEL, PART, LNEW, RAW1, PART1, MODEL1, ERR, OBJS, COUNTER, LNEW8, RAW8, PART8 = (0x100000*k for k in range(1, 16))
+OUT_VALUE, OUT_ERROR, OUT_CHI2 = 1, 2, 4
 
 
 def _put(mem, addr, arr):
@@ -42,9 +43,9 @@ def _get(mem, addr, shape, dtype=np.float32):
     return np.array([mem.get(addr + 4*i, 0) for i in range(n)], np.uint32).view(dtype).reshape(shape)
 
 
-def _render_args(cfg, pcs, nk, value, partial, ngroups, mode):
+def _render_args(cfg, pcs, nk, value, partial, ngroups, mode, error=0, objs=0, tail=(0, 0, 0.0)):
     # lcu_render_args of kernel/lensed.cu: pcs, k0, nk, objs, value, error, image, weight, chimap, partial, ngroups, mode, tail
-    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, 0, nk, 0, value, 0, IMG, WGT, 0, partial, ngroups, mode, 0, 0, 0.0)
+    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, 0, nk, objs, value, error, IMG, WGT, 0, partial, ngroups, mode, *tail)
     return a + b"\0"*(128 - len(a))
 
 
@@ -75,7 +76,7 @@ def _program(cfg, L):
     ctx = L.Context(device=-1)
     try:
         m = cfg.product(ctx, flags=L.LCU_SOURCE_ONLY)
-        text, words, pcs = m.source, m.words, None
+        text, words = m.source, m.words
     finally:
         ctx.close()
     return E.Module(R._compile_ptx(text, 0)), text, words
@@ -116,6 +117,24 @@ def test_render_and_reduce_without_psf():
     # two rays per thread: the one-ray kernel's bits, values and chi^2 partial sums
     assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32))
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
+    # the small-image path (single-point latency): eight warps share a 32-pixel group's quadrature points, object
+    # blocks from global memory, and the block that finishes last adds the partial sums up itself
+    # (lcu_fused_reduce: a counter, a fence) -- same image, same sums, same log-likelihood bits
+    _put(mem, OBJS, np.array(block, np.uint32))
+    M.launch("lcu_render_s8", ((npix + 31)//32, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW8, PART8, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS, tail=(LNEW8, COUNTER, -0.5))],
+             mem, consts)
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW8, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART8, (2*ngroups,)).view(np.uint32))
+    assert np.array_equal(_get(mem, LNEW, (2,)).view(np.uint32), _get(mem, LNEW8, (2,)).view(np.uint32))
+    assert mem.get(COUNTER, 0) == 0                                  # left at zero for the next launch
+    # the quadrature error image (the dumper's ERR layer) from the pair kernel
+    M.launch("lcu_render_pair_err", ((npix + 511)//512, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW1, 0, ngroups, OUT_VALUE | OUT_ERROR, error=ERR)], mem, consts)
+    ref_err = np.asarray(om.render(cfg.params)[1])
+    e = np.abs(_get(mem, ERR, (h, w)).astype(np.float64) - ref_err)/np.maximum(np.abs(ref_model), 1e-30)
+    assert e.max() <= 1e-4, e.max()                                  # alternating-sign weights: on the scale of the value
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32))
 
 
 def test_render_convolve_reduce_with_psf():
