@@ -72,14 +72,14 @@ def _scene(psf):
     return cfg, L
 
 
-def _program(cfg, L):
+def _program(cfg, L, extra=()):
     ctx = L.Context(device=-1)
     try:
         m = cfg.product(ctx, flags=L.LCU_SOURCE_ONLY)
         text, words = m.source, m.words
     finally:
         ctx.close()
-    return E.Module(R._compile_ptx(text, 0)), text, words
+    return E.Module(R._compile_ptx(text, 0, extra)), text, words
 
 
 def _object_block(M, text, cfg, words):
@@ -169,4 +169,36 @@ def test_render_convolve_reduce_with_psf():
     assert abs(lnew - ref_l) <= 1e-6*abs(ref_l), (lnew, ref_l)
     # the small-launch convolution kernel: same bits, image and partial sums
     assert np.array_equal(_get(mem, MODEL, (npix,)).view(np.uint32), _get(mem, MODEL1, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
+
+
+def test_power_law_lens_with_written_out_pair_math():
+    """epl_plus_shear + sersic through lcu_render_pair built with
+    -DLCU_PF_LIBM_PAIR=1 (atan2 / sincos / powr of pairs as packed arithmetic,
+    off by default): the one-ray kernel's bits, the oracle's image."""
+    from lensed_b200 import api
+    base = H.golden_config("epl_plus_shear")
+    h, w = 8, 12
+    params = base.params.copy()
+    params[:8] = [6.3, 4.2, 2.0, 1.2, 0.7, 40.0, 0.03, -0.02]         # lens x y r t q pa g1 g2
+    params[8:15] = [6.8, 4.5, 1.0, -3.0, 1.5, 0.7, 100.0]            # source x y r mag n q pa
+    cfg = dataclasses.replace(base, name="tiny-epl", params=params, image=np.zeros((h, w), np.float32),
+                              weight=np.ones((h, w), np.float32), rule="sub2", psf=None)
+    import lensed_b200 as L
+    M, text, words = _program(cfg, L, ["-DLCU_PF_LIBM_PAIR=1"])
+    assert sum("fma.rn.ftz.f32x2" in line for line in M.functions["lcu_render_pair"].body) > 40   # the packed libm is in
+    block = _object_block(M, text, cfg, words)
+    npix, ngroups = h*w, (h*w + 31)//32
+    qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
+    consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW, PART, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_render_s1", ((npix + 255)//256, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW1, PART1, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    ref = np.asarray(cfg.oracle().render(cfg.params)[0])
+    assert H.rel_err(_get(mem, RAW, (h, w)), ref).max() <= 1e-5
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32))
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))

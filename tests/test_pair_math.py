@@ -231,3 +231,34 @@ def test_default_build_calls_libdevice_lane_by_lane(ptx_default, ptx_packed):
         for ptx, packed in ((ptx_default, False), (ptx_packed, True)):
             entry = re.search(r"\.visible\s+\.entry\s+p_%s\b.*?\n\}" % name, ptx, re.S).group(0)
             assert ("f32x2" in entry) == packed, (name, packed)
+
+
+def test_interpreter_fast_path_is_the_exact_path():
+    """add / sub / mul / fma of normal numbers go through binary64 when that is
+    provably exact; the result must be what exact rational arithmetic gives
+    (near-cancellations, operands far apart, results next to the subnormal and
+    overflow thresholds included)"""
+    rng = random.Random(17)
+
+    def draw():
+        r = rng.random()
+        if r < 0.4:
+            return _u(rng, -4, 4)
+        if r < 0.7:
+            return _lu(rng, 1e-38, 3e38)
+        if r < 0.9:
+            return rng.getrandbits(32)
+        return rng.choice(SPECIAL)
+    fast = 0
+    for _ in range(10000):
+        a, b, c = draw(), draw(), draw()
+        if rng.random() < 0.2:
+            b = a ^ 0x80000000 ^ rng.getrandbits(3)                  # near-cancellation in add, ties in fma
+        for op in ("add", "sub", "mul", "fma"):
+            cc = c if op == "fma" else None
+            for flush in (False, True):
+                want = E._arith_exact(op, a, b, cc, "rn", flush)
+                got = E._arith(op, a, b, cc, "rn", flush)
+                assert got == want, (op, hex(a), hex(b), hex(c), flush, hex(got), hex(want))
+            fast += E._fast_rn(op, a, b, cc) is not None
+    assert fast > 10000                                              # the fast path does take most ordinary cases

@@ -195,8 +195,50 @@ def round_frac(x: Fraction, mode: str = "rn", flush: bool = False, neg_zero: boo
     return sign | (ebits << 23) | (n & 0x007FFFFF)
 
 
+_MIN_NORMAL = 2.0 ** -126
+
+
+def _normal(b: int) -> bool:
+    return 0 < (b & 0x7F800000) < 0x7F800000
+
+
+def _fast_rn(op: str, a: int, b: int, c):
+    """add / sub / mul / fma in round-to-nearest for normal operands and a normal
+    result, through binary64: the product of two binary32 numbers is exact in
+    binary64, and a sum is used only when the error-free transformation says
+    it is exact too -- then the single rounding to binary32 is the operation's.
+    Returns None when the case is not covered (the exact rational path takes it)."""
+    if not (_normal(a) and _normal(b) and (c is None or _normal(c))):
+        return None
+    x, y = b2f(a), b2f(b)
+    if op == "mul":
+        r = x*y
+    else:
+        if op == "fma":
+            x, y = x*y, b2f(c)
+        elif op == "sub":
+            y = -y
+        r = x + y
+        t = r - x
+        if (x - (r - t)) + (y - t) != 0.0:
+            return None
+    if not _MIN_NORMAL <= abs(r) < 3.4e38:
+        return None                                # zero, subnormal or overflowing results: signs, flushing, infinities
+    bits = f2b(r)
+    return bits if _normal(bits) else None
+
+
 def _arith(op: str, a: int, b: int, c: int | None, mode: str, flush: bool) -> int:
     """add / sub / mul / fma on bit patterns"""
+    if mode == "rn":
+        r = _fast_rn(op, a, b, c)
+        if r is not None:
+            return r
+    return _arith_exact(op, a, b, c, mode, flush)
+
+
+def _arith_exact(op: str, a: int, b: int, c: int | None, mode: str, flush: bool) -> int:
+    """the same through exact rational arithmetic: every rounding mode, special values, signed zeros, flushing"""
     if flush:
         a, b = ftz(a), ftz(b)
         if c is not None:
@@ -560,6 +602,10 @@ class Module:
                 raise RuntimeError("deadlock in %s: threads wait at %s" % (fn.name, {e[0] for e in waiting.values()}))
 
 
+_DECODED = {}          # instruction text -> (guard predicate, opcode, operand text, text without the guard)
+_OPERANDS = {}         # instruction text without guard -> (name, modifiers, operands, ftz, rounding mode, type)
+
+
 class _Machine:
     special = {}
 
@@ -624,15 +670,18 @@ class _Machine:
             steps += 1
             if steps > max_steps:
                 raise RuntimeError("step limit in " + self.fn.name)
-            line = insns[pc].rstrip(";").strip()
+            dec = _DECODED.get(insns[pc])
+            if dec is None:
+                line = insns[pc].rstrip(";").strip()
+                guard = re.match(r"^@(!?%p\d+)\s+(.*)$", line)
+                if guard:
+                    line = guard.group(2)
+                op, rest = (re.split(r"\s+", line, maxsplit=1) + [""])[:2]
+                dec = _DECODED[insns[pc]] = (guard.group(1) if guard else None, op, rest.strip(), line)
             pc += 1
-            guard = re.match(r"^@(!?%p\d+)\s+(.*)$", line)
-            if guard:
-                if not self.pred(guard.group(1)):
-                    continue
-                line = guard.group(2)
-            op, rest = (re.split(r"\s+", line, maxsplit=1) + [""])[:2]
-            rest = rest.strip()
+            gpred, op, rest, line = dec
+            if gpred is not None and not self.pred(gpred):
+                continue
             if op in ("ret", "exit"):
                 return
             if op in ("bra", "bra.uni"):
@@ -652,14 +701,15 @@ class _Machine:
             self.step(op, rest, line)
 
     def step(self, op: str, rest: str, line: str):
-        parts = op.split(".")
-        name, mods = parts[0], parts[1:]
-        # operands: split on commas outside braces
-        args = [a.strip() for a in re.split(r",\s*(?![^{]*\})", rest)]
+        dec = _OPERANDS.get(line)
+        if dec is None:
+            parts = op.split(".")
+            mods = parts[1:]
+            # operands: split on commas outside braces
+            dec = _OPERANDS[line] = (parts[0], mods, [a.strip() for a in re.split(r",\s*(?![^{]*\})", rest)], "ftz" in mods,
+                                     next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn"), mods[-1] if mods else "")
+        name, mods, args, flush, mode, typ = dec
         R = self.reg
-        flush = "ftz" in mods
-        mode = next((m for m in mods if m in ("rn", "rz", "rm", "rp")), "rn")
-        typ = mods[-1] if mods else ""
 
         if name == "call":
             m = re.match(r"^(?:\((\w+)\)\s*,)?\s*(\w+)\s*,\s*\(([^)]*)\)$", rest)
