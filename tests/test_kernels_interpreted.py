@@ -43,9 +43,9 @@ def _get(mem, addr, shape, dtype=np.float32):
     return np.array([mem.get(addr + 4*i, 0) for i in range(n)], np.uint32).view(dtype).reshape(shape)
 
 
-def _render_args(cfg, pcs, nk, value, partial, ngroups, mode, error=0, objs=0, tail=(0, 0, 0.0)):
+def _render_args(cfg, pcs, nk, value, partial, ngroups, mode, error=0, objs=0, tail=(0, 0, 0.0), k0=0):
     # lcu_render_args of kernel/lensed.cu: pcs, k0, nk, objs, value, error, image, weight, chimap, partial, ngroups, mode, tail
-    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, 0, nk, objs, value, error, IMG, WGT, 0, partial, ngroups, mode, *tail)
+    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, k0, nk, objs, value, error, IMG, WGT, 0, partial, ngroups, mode, *tail)
     return a + b"\0"*(128 - len(a))
 
 
@@ -202,3 +202,36 @@ def test_power_law_lens_with_written_out_pair_math():
     assert H.rel_err(_get(mem, RAW, (h, w)), ref).max() <= 1e-5
     assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32))
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
+
+
+def test_batch_index_and_row_strip():
+    """blockIdx.y is the parameter point (object blocks and outputs strided by
+    point); a launch restricted to image rows [2, 7) -- how lcu_model_set_rows
+    shards very large images over GPUs -- writes the same bits into those rows."""
+    from lensed_b200 import api
+    cfg, L = _scene(None)
+    M, text, words = _program(cfg, L)
+    second = dataclasses.replace(cfg, params=cfg.params*np.float32(1.01))
+    blocks = _object_block(M, text, cfg, words) + _object_block(M, text, second, words)
+    h, w = cfg.image.shape
+    npix, ngroups = h*w, (h*w + 31)//32
+    qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
+    consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": blocks}
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    M.launch("lcu_render_pair", (1, 2), 256, [_render_args(cfg, cfg.pcs, npix, RAW, PART, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_reduce", (2,), 256, [ngroups, PART, E.d2b(-0.5), LNEW], mem)
+    full = _get(mem, RAW, (2, h, w))
+    lnew = _get(mem, LNEW, (2,), np.float64)
+    for b, c in enumerate((cfg, second)):
+        ref_l, ref_model, _ = c.oracle().loglike(c.params, want_maps=True)
+        assert H.rel_err(full[b], ref_model).max() <= 1e-5
+        assert abs(lnew[b] - ref_l) <= 1e-6*abs(ref_l)
+    assert not np.array_equal(full[0], full[1])
+    r0, r1 = 2, 7
+    M.launch("lcu_render_pair", (1, 2), 256,
+             [_render_args(cfg, cfg.pcs, (r1 - r0)*w, RAW1, PART1, ((r1 - r0)*w + 31)//32, OUT_VALUE | OUT_CHI2, k0=r0*w)], mem, consts)
+    strip = _get(mem, RAW1, (2, h, w))
+    assert np.array_equal(strip[:, r0:r1].view(np.uint32), full[:, r0:r1].view(np.uint32))
+    assert not strip[:, :r0].any() and not strip[:, r1:].any()       # nothing outside the strip is touched
