@@ -212,7 +212,14 @@ def test_batch_index_and_row_strip():
     cfg, L = _scene(None)
     M, text, words = _program(cfg, L)
     second = dataclasses.replace(cfg, params=cfg.params*np.float32(1.01))
-    blocks = _object_block(M, text, cfg, words) + _object_block(M, text, second, words)
+    # the object blocks of both points from the set_params kernel itself (one thread per point)
+    PARAMS = 0x100000*20
+    mem0 = {}
+    _put(mem0, PARAMS, np.concatenate([cfg.params, second.params]).astype(np.float32))
+    M.launch("lcu_set_params", (1,), 64, [2, PARAMS, OBJS], mem0)
+    blocks = [int(v) for v in _get(mem0, OBJS, (2*words,), np.uint32)]
+    assert blocks[:words] == _object_block(M, text, cfg, words) and blocks[words:] == _object_block(M, text, second, words)
+    assert blocks[:words] != blocks[words:]
     h, w = cfg.image.shape
     npix, ngroups = h*w, (h*w + 31)//32
     qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
