@@ -242,3 +242,28 @@ def test_batch_index_and_row_strip():
     strip = _get(mem, RAW1, (2, h, w))
     assert np.array_equal(strip[:, r0:r1].view(np.uint32), full[:, r0:r1].view(np.uint32))
     assert not strip[:, :r0].any() and not strip[:, r1:].any()       # nothing outside the strip is touched
+
+
+def test_weight_map_on_the_device():
+    """lcu_make_weight: gain / (image + offset) in double, narrowed once, masked
+    pixels zero -- the bits of make_weight() + the mask loop (src/data.c:314-330,
+    src/lensed.c:470-482), with a gain value and with a gain map"""
+    cfg, L = _scene(None)
+    M, _, _ = _program(cfg, L)
+    h, w = cfg.image.shape
+    n = h*w
+    rng = np.random.default_rng(2)
+    gain_map = rng.uniform(500, 3000, (h, w)).astype(np.float32)
+    mask = (rng.random((h, w)) < 0.2).astype(np.int32)
+    offset = 2.9633
+    GAIN, MASK, OUT = 0x100000*21, 0x100000*22, 0x100000*23
+    for use_map in (False, True):
+        mem = {}
+        _put(mem, IMG, cfg.image)
+        _put(mem, GAIN, gain_map)
+        _put(mem, MASK, mask)
+        M.launch("lcu_make_weight", (2,), 256, [n, IMG, GAIN if use_map else 0, E.f2b(1800.0), E.d2b(offset), MASK, OUT], mem)
+        gain = gain_map if use_map else np.float32(1800.0)
+        ref = (np.asarray(gain, np.float32).astype(np.float64)/(cfg.image.astype(np.float64) + offset)).astype(np.float32)
+        ref = np.where(mask != 0, np.float32(0), ref)
+        assert np.array_equal(_get(mem, OUT, (h, w)).view(np.uint32), ref.view(np.uint32))

@@ -838,10 +838,11 @@ class _Machine:
                 else:
                     R[args[0]] = (a if x > y else b) if name == "max" else (a if x < y else b)
             return
-        if name in ("max", "min") and typ in ("u32", "s32"):
-            cv = _s32 if typ == "s32" else (lambda v: v & M32)
-            a, b = cv(self.val(args[1])), cv(self.val(args[2]))
-            R[args[0]] = (max(a, b) if name == "max" else min(a, b)) & M32
+        if name in ("max", "min") and typ in ("u32", "s32", "u64", "s64"):
+            w = int(typ[1:])
+            cv = (_s64 if w == 64 else _s32) if typ[0] == "s" else (lambda v: v & ((1 << w) - 1))
+            a, b = cv(self.val(args[1], w)), cv(self.val(args[2], w))
+            R[args[0]] = (max(a, b) if name == "max" else min(a, b)) & ((1 << w) - 1)
             return
         if name in ("rcp", "rsqrt", "ex2", "lg2") and "approx" in mods:
             R[args[0]] = _approx(name, self.val(args[1]), flush)
@@ -927,8 +928,8 @@ class _Machine:
             return
         if name in ("membar", "fence"):
             return
-        if name == "neg" and typ == "s32":
-            R[args[0]] = (-self.val(args[1])) & M32
+        if name == "neg" and typ in ("s32", "s64"):
+            R[args[0]] = (-self.val(args[1], 64)) & (M64 if typ == "s64" else M32)
             return
         if name == "mul" and "wide" in mods:
             a, b = self.val(args[1]), self.val(args[2])
