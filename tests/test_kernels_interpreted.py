@@ -267,3 +267,34 @@ def test_weight_map_on_the_device():
         ref = (np.asarray(gain, np.float32).astype(np.float64)/(cfg.image.astype(np.float64) + offset)).astype(np.float32)
         ref = np.where(mask != 0, np.float32(0), ref)
         assert np.array_equal(_get(mem, OUT, (h, w)).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_convolution_kernels_on_random_shapes(seed):
+    """both convolution kernels on a random image / PSF shape (odd and even
+    PSF sizes, widths that are not a multiple of the tile): the oracle's
+    convolution bit for bit, equal chi^2 partial sums"""
+    import lensed_b200 as L
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+    pw, ph = int(rng.integers(1, 8)), int(rng.integers(1, 8))
+    psf = H.workloads.normalise_psf(rng.random((ph, pw)).astype(np.float32) + 0.1)
+    cfg = dataclasses.replace(H.golden_config("sky"), name="conv-%d" % seed, image=rng.random((h, w)).astype(np.float32),
+                              weight=(rng.random((h, w)) + 0.5).astype(np.float32), rule="point", psf=psf)
+    M, _, _ = _program(cfg, L)
+    raw = rng.random((h, w)).astype(np.float32)*10
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    _put(mem, RAW, raw)
+    gpr = (w + 31)//32
+    ngroups = h*gpr
+    consts = {"lcu_psf": psf.view(np.uint32).ravel()}
+    M.launch("lcu_convolve", ((w + 63)//64, (h + 31)//32, 1), 256,
+             [_convolve_args(RAW, MODEL, PART, h, ngroups, gpr, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_convolve_small", ((w + 31)//32, (h + 7)//8, 1), 256,
+             [_convolve_args(RAW, MODEL1, PART1, h, ngroups, gpr, OUT_VALUE | OUT_CHI2)], mem, consts)
+    ref = np.asarray(cfg.oracle().convolve(raw), np.float32).view(np.uint32)
+    assert np.array_equal(_get(mem, MODEL, (h, w)).view(np.uint32), ref), (w, h, pw, ph)
+    assert np.array_equal(_get(mem, MODEL1, (h, w)).view(np.uint32), ref), (w, h, pw, ph)
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
