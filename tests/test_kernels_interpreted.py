@@ -298,3 +298,50 @@ def test_convolution_kernels_on_random_shapes(seed):
     assert np.array_equal(_get(mem, MODEL, (h, w)).view(np.uint32), ref), (w, h, pw, ph)
     assert np.array_equal(_get(mem, MODEL1, (h, w)).view(np.uint32), ref), (w, h, pw, ph)
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
+
+
+@pytest.mark.parametrize("seed,libm", [(1, False), (4, False), (101, True), (102, True)])
+def test_random_models_through_the_render_kernels(seed, libm):
+    """random object combinations (optional host, one or two lenses, one or two
+    sources, sky) in a small frame: the pair kernel writes the one-ray kernel's
+    bits and both reproduce the oracle within the GPU tests' bound; seeds 101 /
+    102 draw power-law lenses and run with -DLCU_PF_LIBM_PAIR=1.  (A wider sweep
+    of this test -- 24 seeds, 50 convolution shapes -- was run once by hand.)"""
+    import lensed_b200 as L
+    from lensed_b200 import api
+    rng = np.random.default_rng(seed)
+    h, w = int(rng.integers(6, 14)), int(rng.integers(8, 20))
+    objects, params = [], []
+
+    def add(name, role):
+        objects.append(name)
+        params.extend(H._random_params(rng, name, w, h, role))
+    if rng.random() < 0.3:
+        add(str(rng.choice(H.SOURCES)), "host")
+    for _ in range(int(rng.integers(1, 3))):
+        add(str(rng.choice(H.LENSES)), "lens")
+    for _ in range(int(rng.integers(1, 3))):
+        add(str(rng.choice(H.SOURCES)), "source")
+    if rng.random() < 0.7:
+        add("sky", "sky")
+    cfg = H.Config(name="random-tiny-%d" % seed, objects=objects, params=np.array(params, np.float32),
+                   image=np.zeros((h, w), np.float32), weight=np.ones((h, w), np.float32),
+                   rule=str(rng.choice(["point", "sub2"])), psf=None)
+    assert not libm or any(o.startswith("epl") for o in objects)
+    M, text, words = _program(cfg, L, ["-DLCU_PF_LIBM_PAIR=1"] if libm else [])
+    block = _object_block(M, text, cfg, words)
+    npix, ngroups = h*w, (h*w + 31)//32
+    qq, ww = api.quad_rule(cfg.rule, 1, 1)
+    consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
+    mem = {}
+    _put(mem, IMG, cfg.image)
+    _put(mem, WGT, cfg.weight)
+    M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW, PART, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    M.launch("lcu_render_s1", ((npix + 255)//256, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW1, PART1, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
+    ref = np.asarray(cfg.oracle().render(cfg.params)[0])
+    floor = H.rel_err(ref, np.asarray(cfg.oracle("f64").render(cfg.params)[0], np.float64)).max()
+    assert H.rel_err(_get(mem, RAW, (h, w)), ref).max() <= max(1e-5, 1.5*floor), objects
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW1, (npix,)).view(np.uint32)), objects
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART1, (2*ngroups,)).view(np.uint32))
