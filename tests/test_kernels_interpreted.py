@@ -128,6 +128,11 @@ def test_render_and_reduce_without_psf():
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART8, (2*ngroups,)).view(np.uint32))
     assert np.array_equal(_get(mem, LNEW, (2,)).view(np.uint32), _get(mem, LNEW8, (2,)).view(np.uint32))
     assert mem.get(COUNTER, 0) == 0                                  # left at zero for the next launch
+    # four warps per group, no fused tail: partial sums for lcu_reduce
+    M.launch("lcu_render_s4", ((npix + 63)//64, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAW8, PART8, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS)], mem, consts)
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW8, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART8, (2*ngroups,)).view(np.uint32))
     # the quadrature error image (the dumper's ERR layer) from the pair kernel
     M.launch("lcu_render_pair_err", ((npix + 511)//512, 1), 256,
              [_render_args(cfg, cfg.pcs, npix, RAW1, 0, ngroups, OUT_VALUE | OUT_ERROR, error=ERR)], mem, consts)
