@@ -3,7 +3,8 @@
 `tools/ptx_emu.py` executes NVRTC's PTX of a model's program as a grid of
 thread blocks (threads as coroutines that meet at `bar.sync` and, per warp, at
 `shfl.sync`; global, constant, shared and parameter memory; exact IEEE
-arithmetic).  That is enough to run the whole evaluation of a small image --
+arithmetic; loads from addresses nobody wrote raise, so out-of-bounds and
+uninitialised reads show as they would under compute-sanitizer).  That is enough to run the whole evaluation of a small image --
 `lcu_set_params`' body, `lcu_render_pair[_err]`, `lcu_render_s1`, `lcu_render_s8`
 with the fused final reduction, `lcu_convolve` / `lcu_convolve_small` with the
 fused chi^2, `lcu_reduce` -- and hold the result
@@ -40,7 +41,7 @@ def _put(mem, addr, arr):
 
 def _get(mem, addr, shape, dtype=np.float32):
     n = int(np.prod(shape))*np.dtype(dtype).itemsize//4
-    return np.array([mem.get(addr + 4*i, 0) for i in range(n)], np.uint32).view(dtype).reshape(shape)
+    return np.array([dict.get(mem, addr + 4*i, 0) for i in range(n)], np.uint32).view(dtype).reshape(shape)
 
 
 def _render_args(cfg, pcs, nk, value, partial, ngroups, mode, error=0, objs=0, tail=(0, 0, 0.0), k0=0):
@@ -99,7 +100,7 @@ def test_render_and_reduce_without_psf():
     npix, ngroups = h*w, (h*w + 31)//32
     qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
     consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
@@ -121,13 +122,14 @@ def test_render_and_reduce_without_psf():
     # blocks from global memory, and the block that finishes last adds the partial sums up itself
     # (lcu_fused_reduce: a counter, a fence) -- same image, same sums, same log-likelihood bits
     _put(mem, OBJS, np.array(block, np.uint32))
+    mem[COUNTER] = 0                                                 # the runtime allocates the counters zeroed
     M.launch("lcu_render_s8", ((npix + 31)//32, 1), 256,
              [_render_args(cfg, cfg.pcs, npix, RAW8, PART8, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS, tail=(LNEW8, COUNTER, -0.5))],
              mem, consts)
     assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW8, (npix,)).view(np.uint32))
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART8, (2*ngroups,)).view(np.uint32))
     assert np.array_equal(_get(mem, LNEW, (2,)).view(np.uint32), _get(mem, LNEW8, (2,)).view(np.uint32))
-    assert mem.get(COUNTER, 0) == 0                                  # left at zero for the next launch
+    assert mem[COUNTER] == 0                                         # left at zero for the next launch
     # four warps per group, no fused tail: partial sums for lcu_reduce
     M.launch("lcu_render_s4", ((npix + 63)//64, 1), 256,
              [_render_args(cfg, cfg.pcs, npix, RAW8, PART8, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS)], mem, consts)
@@ -154,7 +156,7 @@ def test_render_convolve_reduce_with_psf():
     qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
     consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block,
               "lcu_psf": psf.astype(np.float32).view(np.uint32).ravel()}
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
@@ -196,7 +198,7 @@ def test_power_law_lens_with_written_out_pair_math():
     npix, ngroups = h*w, (h*w + 31)//32
     qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
     consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,
@@ -219,7 +221,7 @@ def test_batch_index_and_row_strip():
     second = dataclasses.replace(cfg, params=cfg.params*np.float32(1.01))
     # the object blocks of both points from the set_params kernel itself (one thread per point)
     PARAMS = 0x100000*20
-    mem0 = {}
+    mem0 = E.StrictMemory()
     _put(mem0, PARAMS, np.concatenate([cfg.params, second.params]).astype(np.float32))
     M.launch("lcu_set_params", (1,), 64, [2, PARAMS, OBJS], mem0)
     blocks = [int(v) for v in _get(mem0, OBJS, (2*words,), np.uint32)]
@@ -229,7 +231,7 @@ def test_batch_index_and_row_strip():
     npix, ngroups = h*w, (h*w + 31)//32
     qq, ww = api.quad_rule(cfg.rule, cfg.pcs[2], cfg.pcs[3])
     consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": blocks}
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     M.launch("lcu_render_pair", (1, 2), 256, [_render_args(cfg, cfg.pcs, npix, RAW, PART, ngroups, OUT_VALUE | OUT_CHI2)], mem, consts)
@@ -263,7 +265,7 @@ def test_weight_map_on_the_device():
     offset = 2.9633
     GAIN, MASK, OUT = 0x100000*21, 0x100000*22, 0x100000*23
     for use_map in (False, True):
-        mem = {}
+        mem = E.StrictMemory()        # a load from an address nobody wrote raises
         _put(mem, IMG, cfg.image)
         _put(mem, GAIN, gain_map)
         _put(mem, MASK, mask)
@@ -288,7 +290,7 @@ def test_convolution_kernels_on_random_shapes(seed):
                               weight=(rng.random((h, w)) + 0.5).astype(np.float32), rule="point", psf=psf)
     M, _, _ = _program(cfg, L)
     raw = rng.random((h, w)).astype(np.float32)*10
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     _put(mem, RAW, raw)
@@ -338,7 +340,7 @@ def test_random_models_through_the_render_kernels(seed, libm):
     npix, ngroups = h*w, (h*w + 31)//32
     qq, ww = api.quad_rule(cfg.rule, 1, 1)
     consts = {"lcu_quad": np.c_[qq, ww].astype(np.float32).view(np.uint32).ravel(), "lcu_objs_c": block}
-    mem = {}
+    mem = E.StrictMemory()        # a load from an address nobody wrote raises
     _put(mem, IMG, cfg.image)
     _put(mem, WGT, cfg.weight)
     M.launch("lcu_render_pair", ((npix + 511)//512, 1), 256,

@@ -424,6 +424,22 @@ def _round_int(fr: Fraction, mode: str) -> int:
 # ---------------------------------------------------------------------------
 # the interpreter
 # ---------------------------------------------------------------------------
+class StrictMemory(dict):
+    """address -> word memory for Module.launch / Module.run in which a load from
+    an address nobody has written raises (a plain dict reads such words as
+    zero): out-of-bounds and uninitialised reads of the kernels -- global and
+    shared memory alike -- surface the way compute-sanitizer's initcheck and
+    memcheck show them on a device.  Read results back with `peek`."""
+
+    def get(self, key, default=None):
+        if key not in self:
+            raise KeyError("load from unwritten address %#x" % key)
+        return self[key]
+
+    def peek(self, key, default=0):
+        return dict.get(self, key, default)
+
+
 class Function:
     def __init__(self, name, params, body):
         self.name, self.params, self.body = name, params, body
