@@ -262,3 +262,42 @@ def test_interpreter_fast_path_is_the_exact_path():
                 assert got == want, (op, hex(a), hex(b), hex(c), flush, hex(got), hex(want))
             fast += E._fast_rn(op, a, b, cc) is not None
     assert fast > 10000                                              # the fast path does take most ordinary cases
+
+
+RACY = """
+.visible .entry k_race(.param .u64 k_race_param_0)
+{
+    .shared .align 4 .b8 buf[8];
+    ld.param.u64 %rd1, [k_race_param_0];
+    mov.u32 %r1, %tid.x;
+    mov.u32 %r2, buf;
+    st.shared.u32 [buf], %r1;
+    RACE_BAR
+    ld.shared.u32 %r3, [buf];
+    st.global.u32 [%rd1], %r3;
+    ret;
+}
+.visible .entry k_oob(.param .u64 k_oob_param_0)
+{
+    ld.param.u64 %rd1, [k_oob_param_0];
+    ld.global.u32 %r1, [%rd1+4096];
+    st.global.u32 [%rd1], %r1;
+    ret;
+}
+"""
+
+
+def test_interpreter_flags_races_and_unwritten_loads():
+    """negative controls for the two checks the interpreted kernel tests rely on:
+    two threads writing one shared word without a barrier, and a load from an
+    address nobody wrote, both raise"""
+    M = E.Module(RACY.replace("RACE_BAR", ""))
+    with pytest.raises(RuntimeError, match="shared-memory hazard"):
+        M.launch("k_race", (1,), 2, [0x1000], E.StrictMemory())
+    M.launch("k_race", (1,), 1, [0x1000], E.StrictMemory())          # one thread: nothing to race with
+    M.launch("k_race", (1,), 2, [0x1000], E.StrictMemory(), racecheck=False)
+    with pytest.raises(KeyError, match="unwritten address"):
+        M.launch("k_oob", (1,), 1, [0x1000], E.StrictMemory())
+    mem = {}
+    M.launch("k_oob", (1,), 1, [0x1000], mem)                        # a plain dict reads zeros
+    assert mem[0x1000] == 0

@@ -526,14 +526,18 @@ class Module:
         return [mem.get(out_addr + 4 * i) for i in range(n_out)]
 
 
-    def launch(self, name: str, grid, block, params, mem, consts=None, max_steps: int = 5_000_000):
+    def launch(self, name: str, grid, block, params, mem, consts=None, max_steps: int = 5_000_000, racecheck: bool = True):
         """Run kernel `name` over a grid (x, y, z) of blocks of `block` threads.
         params: one entry per kernel parameter -- an int for a scalar, bytes for a
         struct passed by value.  mem: the address -> 32-bit word dictionary shared
         by all threads (global memory; the caller places its buffers in it).
         consts: __constant__ arrays by name (lists of 32-bit words).  Threads of a
         block run as coroutines that meet at bar.sync and, per warp, at shfl.sync:
-        enough for kernels whose warps are converged at those points."""
+        enough for kernels whose warps are converged at those points.
+        racecheck: shared-memory hazards between two threads of a block without a
+        bar.sync in between (write after write, read after write, write after
+        read) raise -- threads run one after the other here, so a kernel with such
+        a hazard would give an order-dependent answer that proves nothing."""
         fn = self.functions[name]
         for addr, data in self.globals.values():
             for i in range(0, len(data), 4):
@@ -558,12 +562,14 @@ class Module:
                 for bx in range(gx):
                     for a in [k for k in mem if 0x30000000 <= k < 0x30100000]:
                         del mem[a]                 # shared memory does not outlive the block
-                    self._run_block(fn, env, mem, (bx, by, bz), (gx, gy, gz), block, max_steps)
+                    self._run_block(fn, env, mem, (bx, by, bz), (gx, gy, gz), block, max_steps, racecheck)
 
-    def _run_block(self, fn, env, mem, bid, gdim, nthreads, max_steps):
+    def _run_block(self, fn, env, mem, bid, gdim, nthreads, max_steps, racecheck=True):
         threads = []
+        hazards = {} if racecheck else None        # shared address -> [last writer, readers] since the last barrier
         for t in range(nthreads):
             mach = _Machine(self, fn, env, mem)
+            mach.tid, mach.hazards = t, hazards
             mach.special = {"%tid.x": t, "%tid.y": 0, "%tid.z": 0, "%ntid.x": nthreads, "%ntid.y": 1, "%ntid.z": 1,
                             "%ctaid.x": bid[0], "%ctaid.y": bid[1], "%ctaid.z": bid[2],
                             "%nctaid.x": gdim[0], "%nctaid.y": gdim[1], "%nctaid.z": gdim[2],
@@ -613,6 +619,8 @@ class Module:
                 for t in alive:
                     reply[t] = None
                 waiting.clear()
+                if hazards is not None:
+                    hazards.clear()
                 progressed = True
             if not progressed and all(t in waiting for t in alive):
                 raise RuntimeError("deadlock in %s: threads wait at %s" % (fn.name, {e[0] for e in waiting.values()}))
@@ -624,6 +632,25 @@ _OPERANDS = {}         # instruction text without guard -> (name, modifiers, ope
 
 class _Machine:
     special = {}
+    tid, hazards = 0, None
+
+    def shared_access(self, addr: int, write: bool):
+        """racecheck bookkeeping for one 32-bit word of shared memory"""
+        if self.hazards is None or not 0x30000000 <= addr < 0x30100000:
+            return
+        writer, readers = self.hazards.setdefault(addr, [None, set()])
+        if write:
+            if writer not in (None, self.tid):
+                raise RuntimeError("shared-memory hazard in %s: threads %d and %d write %#x without a barrier" % (self.fn.name, writer, self.tid, addr))
+            if readers - {self.tid}:
+                raise RuntimeError("shared-memory hazard in %s: thread %d writes %#x that thread %d read, without a barrier"
+                                   % (self.fn.name, self.tid, addr, min(readers - {self.tid})))
+            self.hazards[addr][0] = self.tid
+        else:
+            if writer not in (None, self.tid):
+                raise RuntimeError("shared-memory hazard in %s: thread %d reads %#x that thread %d wrote, without a barrier"
+                                   % (self.fn.name, self.tid, addr, writer))
+            readers.add(self.tid)
 
     def __init__(self, module, fn, params, mem, depth: int = 0):
         self.module, self.fn, self.params, self.mem = module, fn, params, mem
@@ -758,6 +785,11 @@ class _Machine:
             src = self.params[var] if var in self.params else self.pspace[var]
             R[args[0]] = src[off] if isinstance(src, dict) else src
             return
+        if name == "st" and mods[0] == "shared":
+            a0 = self.addr(args[0])
+            n = len(args[1].split(",")) if args[1].startswith("{") else 1
+            for k in range(n*(2 if typ in ("u64", "b64", "s64", "f64") else 1)):
+                self.shared_access(a0 + 4*k, True)
         if name == "st" and args[1].startswith("{"):          # st.global.v2 / .v4 (32-bit elements)
             a = self.addr(args[0])
             for i, t in enumerate(x.strip() for x in args[1].strip("{}").split(",")):
@@ -765,6 +797,10 @@ class _Machine:
             return
         if name == "ld":
             a = self.addr(args[1])
+            if mods[0] == "shared":
+                n = len(args[0].split(",")) if args[0].startswith("{") else 1
+                for k in range(n*(2 if typ in ("u64", "b64", "s64", "f64") else 1)):
+                    self.shared_access(a + 4*k, False)
             if typ in ("u8", "s8", "b8"):
                 R[args[0]] = self.mem.get(a, 0) & 0xFF
                 return
