@@ -8,8 +8,8 @@
 
 FIRST / LAST are seeds; extra arguments are NVRTC options (e.g. -DLCU_PF_LIBM_PAIR=1).
 Memory is strict (ptx_emu.StrictMemory): a load from an unwritten address raises.
-The results on record (round 1): conv 50 shapes, render 24 models (12 with the
-packed libm switch), full 20 models: no difference beyond the GPU tests' bounds.
+The results on record (round 1): conv 50 shapes, render 84 models (42 with the
+packed libm switch), full 45 models: no difference beyond the GPU tests' bounds.
 """
 import dataclasses
 import os

@@ -113,7 +113,7 @@ function level  tests/test_pair_math.py            atan2 / sincos / sin / cos / 
 ray level       tests/test_pair_rays.py            lcu_compute2 = lcu_compute on rays through the four EPL test configurations and C5,
                                                    also with the reference's own objects/*.cl
 kernel level    tests/test_kernels_interpreted.py  lcu_render_pair = lcu_render_s1 (image and chi^2 partial sums) on an EPL scene and on
-                                                   random models with power-law lenses; 12 more random models by hand
+                                                   random models with power-law lenses; 42 more random models by hand
 ptxas           tests/test_pair_rays.py            packed instruction counts of lcu_render_pair equal in PTX and SASS (no contraction)
 hardware        tests/test_gpu_parity.py           test_two_rays_per_thread_same_bits_with_packed_libm: non-gating (xfail, not strict),
                                                    runs with the GPU suite; XPASS = confirmed""")
