@@ -81,10 +81,13 @@ unsigned long long lcu_launch_count(void);
  * src/opencl.h:42-45).  device >= 0 selects a CUDA device; device < 0
  * creates a compile-only context (no GPU needed).  kernel_dir / objects_dir:
  * where kernel/{shim.cuh,object.cuh,lensed.cu} and objects/<name>.cl live
- * (the reference's LENSED_PATH/kernel and /objects, src/kernel.c:11-13);
- * NULL = the directories shipped next to this library.  objects_dir may be
- * the objects/ directory of a Lensed installation: its files are consumed
- * unmodified.
+ * (the reference's LENSED_PATH/kernel and /objects, src/kernel.c:11-13).
+ * kernel_dir NULL = the kernel/ directory shipped next to this library.
+ * objects_dir is the objects/ directory of a Lensed installation -- its files
+ * are consumed unmodified, and this library ships none of its own; NULL =
+ * $LENSED_PATH/objects (as src/path.c:56-78 resolves it), else objects/ next
+ * to this library.  A missing object file is reported by the call that first
+ * needs it, in the reference's words (src/kernel.c:757-759).
  */
 int lcu_create(int device, const char* kernel_dir, const char* objects_dir, lcu_ctx** ctx);
 void lcu_destroy(lcu_ctx* ctx);

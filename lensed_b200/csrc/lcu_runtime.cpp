@@ -615,7 +615,15 @@ int lcu_create(int device, const char* kernel_dir, const char* objects_dir, lcu_
     lcu_ctx* ctx = new lcu_ctx;
     const std::string base = library_dir();
     ctx->kernel_dir = kernel_dir ? kernel_dir : base + "/kernel";
-    ctx->objects_dir = objects_dir ? objects_dir : base + "/objects";
+    // the library ships no object files: the plugin directory is the caller's
+    // (a Lensed installation's objects/), or $LENSED_PATH/objects as the
+    // reference resolves it (src/kernel.c:11-13, src/path.c:56-78)
+    if(objects_dir)
+        ctx->objects_dir = objects_dir;
+    else if(const char* lp = getenv("LENSED_PATH"))
+        ctx->objects_dir = std::string(lp) + (*lp && lp[strlen(lp) - 1] == '/' ? "" : "/") + "objects";
+    else
+        ctx->objects_dir = base + "/objects";
 
     struct { const char* file; std::string* dst; } files[] = {
         { "shim.cuh", &ctx->shim }, { "object.cuh", &ctx->object_hdr }, { "lensed.cu", &ctx->kernels } };

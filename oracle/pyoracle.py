@@ -24,6 +24,8 @@ _VARIANTS = {
     "fast": "liboracle_fast.so",
     "ref": os.path.join("_ref", "liblensed_ref.so"),
     "ref_fast": os.path.join("_ref", "liblensed_ref_fast.so"),
+    # the same reference text with float = 8 consecutive work-items (AVX2): timing only
+    "ref_simd": os.path.join("_ref", "liblensed_ref_simd.so"),
 }
 
 _libs: dict = {}

@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# the plugin directory of every test: the reference's own objects/*.cl, verbatim
+# (tests/golden/objects/README.md); the library ships no object files
+OBJECTS_DIR = os.path.join(ROOT, "tests", "golden", "objects")
+
 
 def _ensure_built():
     """Built artefacts are git-ignored: on a fresh checkout compile the C-ABI
@@ -33,7 +37,7 @@ def pytest_configure(config):
 def compile_ctx():
     """Compile-only context: NVRTC + metadata, no device."""
     import lensed_b200 as L
-    ctx = L.Context(device=-1)
+    ctx = L.Context(device=-1, objects_dir=OBJECTS_DIR)
     yield ctx
     ctx.close()
 
@@ -41,6 +45,6 @@ def compile_ctx():
 @pytest.fixture(scope="session")
 def gpu_ctx():
     import lensed_b200 as L
-    ctx = L.Context(device=0)
+    ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
     yield ctx
     ctx.close()

@@ -15,6 +15,8 @@ from lensed_b200 import workloads
 from oracle import pyoracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# the reference's objects/*.cl, verbatim: the plugin directory of every test (golden/objects/README.md)
+OBJECTS_DIR = os.path.join(GOLDEN, "objects")
 
 
 @dataclass

@@ -11,6 +11,9 @@ import helpers as H
 from oracle import pyoracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the C host passes objects_dir = NULL: the library looks in $LENSED_PATH/objects, as the
+# reference does (src/kernel.c:11-13); here that is the verbatim copy of the reference's objects/
+ENV = dict(os.environ, LENSED_PATH=os.path.dirname(H.OBJECTS_DIR))
 
 
 @pytest.fixture(scope="module")
@@ -24,7 +27,7 @@ def host_check(tmp_path_factory):
 
 
 def test_metadata_from_c(host_check):
-    out = subprocess.run([host_check, "meta"], check=True, capture_output=True, text=True).stdout.splitlines()
+    out = subprocess.run([host_check, "meta"], check=True, capture_output=True, text=True, env=ENV).stdout.splitlines()
     objs = [l.split() for l in out if l.startswith("object")]
     assert len(objs) == 15
     for f in objs:
@@ -43,7 +46,7 @@ def test_metadata_from_c(host_check):
 @pytest.mark.gpu
 def test_loglike_from_c(host_check):
     size = 64
-    out = subprocess.run([host_check, "loglike", "0", str(size)], check=True, capture_output=True, text=True).stdout.splitlines()
+    out = subprocess.run([host_check, "loglike", "0", str(size)], check=True, capture_output=True, text=True, env=ENV).stdout.splitlines()
     assert out[0] == "model npars 12 words 28"
     lnew = [float(v) for v in out[1].split()[1:]]
     assert lnew[0] == lnew[1]                                  # single == first of the batch
@@ -73,7 +76,7 @@ def test_single_point_latency_from_c(host_check):
     100 x 100 image (the reference's example size).  The reference's CPU build
     takes ~2 ms per call on 16 threads; anything above 200 us here means the
     graph path is not in use."""
-    out = subprocess.run([host_check, "latency", "0", "100", "2000"], check=True, capture_output=True, text=True).stdout
+    out = subprocess.run([host_check, "latency", "0", "100", "2000"], check=True, capture_output=True, text=True, env=ENV).stdout
     print(out)
     us = float(out.split()[1])
     assert 0 < us < 200

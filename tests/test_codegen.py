@@ -6,6 +6,7 @@ import re
 import numpy as np
 import pytest
 
+import helpers as H
 import lensed_b200 as L
 
 IMG = np.zeros((8, 8), np.float32)
@@ -61,7 +62,7 @@ def test_pair_copy_of_every_shipped_object(compile_ctx):
     packed pair of rays (shim.cuh); the model then carries lcu_compute2 and the
     two-rays-per-thread kernels, unless LCU_NO_PAIR asks for one ray."""
     import os
-    names = sorted(f[:-3] for f in os.listdir(os.path.join(os.path.dirname(L.__file__), "objects")) if f.endswith(".cl"))
+    names = sorted(f[:-3] for f in os.listdir(H.OBJECTS_DIR) if f.endswith(".cl"))
     assert len(names) == 15
     for n in names:
         ok, why = compile_ctx.object_pairable(n)
@@ -94,7 +95,7 @@ def test_object_that_cannot_be_paired_falls_back(tmp_path):
     per thread."""
     import shutil
     objdir = tmp_path / "objects"
-    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    shutil.copytree(H.OBJECTS_DIR, objdir)
     (objdir / "ring.cl").write_text(
         "type = SOURCE;\n"
         "params { {\"x\", POSITION_X}, {\"y\", POSITION_Y}, {\"r\", RADIUS} };\n"
@@ -227,7 +228,7 @@ def test_plugin_text_with_comments_macros_helpers_and_qualifiers(tmp_path):
     docs/create.md must survive it -- in the scalar, the setter and the pair copy."""
     import shutil
     objdir = tmp_path / "objects"
-    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    shutil.copytree(H.OBJECTS_DIR, objdir)
     (objdir / "tricky.cl").write_text(TRICKY)
     ctx = L.Context(device=-1, objects_dir=str(objdir))
     try:
@@ -304,7 +305,7 @@ def test_opencl_builtins_a_plugin_may_call(tmp_path):
     the model falls back to one ray per thread."""
     import shutil
     objdir = tmp_path / "objects"
-    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    shutil.copytree(H.OBJECTS_DIR, objdir)
     (objdir / "builtins.cl").write_text(BUILTINS)
     (objdir / "builtins2.cl").write_text("\n".join(l for l in BUILTINS.splitlines() if "isnan(" not in l))
     ctx = L.Context(device=-1, objects_dir=str(objdir))
@@ -327,7 +328,7 @@ def test_object_file_encodings_and_function_specifiers(tmp_path):
     stray ';' after function bodies that docs/create.md:113,149 has."""
     import shutil
     objdir = tmp_path / "objects"
-    src = os.path.join(os.path.dirname(L.__file__), "objects")
+    src = H.OBJECTS_DIR
     shutil.copytree(src, objdir)
     sersic = open(os.path.join(src, "sersic.cl")).read()
     sie = open(os.path.join(src, "sie.cl")).read()
@@ -380,7 +381,7 @@ def test_gentype_builtins_on_vectors(tmp_path):
     too), also in the lens an image-plane prior is shot through."""
     import shutil
     objdir = tmp_path / "objects"
-    shutil.copytree(os.path.join(os.path.dirname(L.__file__), "objects"), objdir)
+    shutil.copytree(H.OBJECTS_DIR, objdir)
     (objdir / "vecfn.cl").write_text(VECTOR_BUILTINS)
     ctx = L.Context(device=-1, objects_dir=str(objdir))
     try:

@@ -546,21 +546,19 @@ def test_two_rays_per_thread_same_bits(gpu_ctx, monkeypatch, flags):
             assert np.array_equal(m2.loglike_batch(P), m1.loglike_batch(P)), cfg.name
 
 
-@pytest.mark.xfail(strict=False, reason="experimental switch -DLCU_PF_LIBM_PAIR=1 (off by default): its first run on hardware; "
-                   "XPASS = ready to become the default (DESIGN.md 4a)")
+@pytest.mark.parametrize("libm_pair", ["0", "1"])
 @pytest.mark.parametrize("flags", MATH_MODES)
-def test_two_rays_per_thread_same_bits_with_packed_libm(gpu_ctx, monkeypatch, flags):
-    """atan2 / sincos / powr of pairs as packed arithmetic: the power-law lens
-    configurations and C5 against the one-ray kernel, bit for bit.  The switch
-    was written after the round's GPU budget was spent and is checked on the CPU
-    only (tests/test_pair_math.py, test_pair_rays.py, test_kernels_interpreted.py);
-    this test neither fails nor gates the suite, it records the hardware's answer."""
+def test_two_rays_per_thread_same_bits_packed_libm_switch(gpu_ctx, monkeypatch, flags, libm_pair):
+    """atan2 / sincos / powr of pairs as packed arithmetic (the default,
+    LCU_PF_LIBM_PAIR=1) and lane by lane through libdevice (=0): the power-law
+    lens configurations and C5 against the one-ray kernel, bit for bit, with the
+    switch in either position."""
     import lensed_b200 as L
     monkeypatch.setenv("LCU_SPLIT", "1")
     cases = [("golden", n) for n in H.golden_names() if n.startswith("epl")] + [("synthetic", ("c5", 96, True))]
     for kind, arg in cases:
         cfg = H.golden_config(arg) if kind == "golden" else H.synthetic_config(*arg[:2], psf=arg[2])
-        monkeypatch.setenv("LCU_NVRTC_FLAGS", "-DLCU_PF_LIBM_PAIR=1")
+        monkeypatch.setenv("LCU_NVRTC_FLAGS", "-DLCU_PF_LIBM_PAIR=" + libm_pair)
         m2 = cfg.product(gpu_ctx, flags=flags)
         monkeypatch.delenv("LCU_NVRTC_FLAGS")
         m1 = cfg.product(gpu_ctx, flags=flags | L.LCU_NO_PAIR)

@@ -74,7 +74,7 @@ def _scene(psf):
 
 
 def _program(cfg, L, extra=()):
-    ctx = L.Context(device=-1)
+    ctx = L.Context(device=-1, objects_dir=H.OBJECTS_DIR)
     try:
         m = cfg.product(ctx, flags=L.LCU_SOURCE_ONLY)
         text, words = m.source, m.words

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import helpers as H
 import lensed_b200 as L
 from oracle import pyoracle as O
 
@@ -38,12 +39,38 @@ def test_sky_gradient_defaults(compile_ctx):
     assert np.signbit(np.float32(p[1].defval)) and p[1].defval == 0
 
 
-@pytest.mark.skipif(not os.path.isdir(REF_OBJECTS), reason="reference tree not present")
-@pytest.mark.parametrize("name", NAMES)
-def test_reference_object_files_unmodified(name):
-    """Drop-in: the reference's objects/ directory compiles as is."""
-    ctx = L.Context(device=-1, objects_dir=REF_OBJECTS)
-    _same(ctx.object_info(name), O.object_info(name))
+def test_fixture_objects_are_the_reference_files():
+    """tests/golden/objects/ -- the plugin directory every test, smoke() and
+    bench.py run on -- holds the reference's objects/*.cl byte for byte: checked
+    against the committed SHA-256 list everywhere and against the reference tree
+    where it exists."""
+    import hashlib
+    sums = dict(reversed(l.split()) for l in open(os.path.join(H.OBJECTS_DIR, "SHA256SUMS")))
+    files = sorted(f for f in os.listdir(H.OBJECTS_DIR) if f.endswith(".cl"))
+    assert files == sorted(sums) and len(files) == 15
+    for f in files:
+        data = open(os.path.join(H.OBJECTS_DIR, f), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == sums[f], f
+        if os.path.isdir(REF_OBJECTS):
+            assert data == open(os.path.join(REF_OBJECTS, f), "rb").read(), f
+    if os.path.isdir(REF_OBJECTS):
+        assert files == sorted(f for f in os.listdir(REF_OBJECTS) if f.endswith(".cl"))
+
+
+def test_library_ships_no_object_files(monkeypatch, tmp_path):
+    """No objects_dir and no LENSED_PATH: the first object load fails in the
+    reference's words (src/kernel.c:757-759); LENSED_PATH/objects is found as the
+    reference finds it (src/kernel.c:11-13)."""
+    assert not os.path.isdir(os.path.join(os.path.dirname(L.__file__), "objects"))
+    monkeypatch.delenv("LENSED_PATH", raising=False)
+    ctx = L.Context(device=-1)
+    with pytest.raises(L.LensedCudaError, match='could not load object "sersic"'):
+        ctx.object_info("sersic")
+    ctx.close()
+    monkeypatch.setenv("LENSED_PATH", os.path.dirname(H.OBJECTS_DIR))
+    ctx = L.Context(device=-1)
+    _same(ctx.object_info("sersic"), O.object_info("sersic"))
+    ctx.close()
 
 
 @pytest.mark.skipif(not O.available("ref"), reason="oracle/_ref not built")

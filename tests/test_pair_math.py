@@ -80,6 +80,12 @@ def ptx_default():
     return _compile_ptx([])
 
 
+@pytest.fixture(scope="module")
+def ptx_lanewise():
+    """atan2 / sincos / powr of pairs lane by lane through libdevice"""
+    return _compile_ptx(["-DLCU_PF_LIBM_PAIR=0"])
+
+
 SPECIAL = [0x00000000, 0x80000000, 0x3F800000, 0xBF800000, 0x7F800000, 0xFF800000, 0x7FC00000, 0x00000001, 0x80000400,
            0x00800000, 0x7F7FFFFF, 0xFF7FFFFF, 0x40000000, 0x3F000000, 0x40400000, 0xC0400000, 0x3F7FFFFF, 0x3F800001,
            0x47CE4780, 0x47CE477F, 0x4B000000, 0x7E000000, 0x0D000000, 0x0CFFFFFF, 0x42B17218, 0xC2CFF1B5]
@@ -224,11 +230,11 @@ def test_comparison_is_sensitive(ptx_packed):
         assert differs > 0, name
 
 
-def test_default_build_calls_libdevice_lane_by_lane(ptx_default, ptx_packed):
-    """the switch is off by default: without it atan2 / sincos / powr of pairs
-    contain no packed instruction, with it they do"""
+def test_default_build_is_the_packed_libm(ptx_default, ptx_packed, ptx_lanewise):
+    """the switch is on by default: atan2 / sincos / powr of pairs are packed
+    instructions unless -DLCU_PF_LIBM_PAIR=0 asks for the lane-by-lane libdevice calls"""
     for name in ("atan2", "sincos", "powr", "sin", "cos"):
-        for ptx, packed in ((ptx_default, False), (ptx_packed, True)):
+        for ptx, packed in ((ptx_default, True), (ptx_packed, True), (ptx_lanewise, False)):
             entry = re.search(r"\.visible\s+\.entry\s+p_%s\b.*?\n\}" % name, ptx, re.S).group(0)
             assert ("f32x2" in entry) == packed, (name, packed)
 

@@ -9,6 +9,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJECTS_DIR = os.path.join(ROOT, "tests", "golden", "objects")      # the reference's objects/*.cl, verbatim
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -18,7 +19,7 @@ import helpers as H  # noqa: E402
 from oracle import pyoracle as O  # noqa: E402
 
 out = {}
-ctx = L.Context(device=0)
+ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 out["fp32_peak_tflops"] = ctx.fp32_peak_tflops()
 print("fp32 peak", out["fp32_peak_tflops"], flush=True)
 print("host threads", O.lib().orc_max_threads(), flush=True)

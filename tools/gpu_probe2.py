@@ -3,12 +3,13 @@
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJECTS_DIR = os.path.join(ROOT, "tests", "golden", "objects")      # the reference's objects/*.cl, verbatim
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import lensed_b200 as L
 from lensed_b200 import workloads
 import helpers as H
 
-ctx = L.Context(device=0)
+ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 cfgs = [H.golden_config(n) for n in ("sie", "epl", "point_mass", "nsie", "sersic", "devauc", "gauss", "sis_plus_shear")]
 cfgs += [H.example_config("test_sersic_bulge"), H.example_config("full_mock_nopsf"), H.example_config("full_mock_psf")]
 cfgs += [H.synthetic_config("c4", 128), H.synthetic_config("c4", 256), H.synthetic_config("c5", 256), H.synthetic_config("c5", 512),

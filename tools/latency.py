@@ -5,12 +5,13 @@ the reference CPU build.  Writes gpurun_out/latency.json."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJECTS_DIR = os.path.join(ROOT, "tests", "golden", "objects")      # the reference's objects/*.cl, verbatim
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import lensed_b200 as L
 import helpers as H
 
 out = {}
-ctx = L.Context(device=0)
+ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
     cfg = H.example_config(name)
     res = {}

@@ -15,6 +15,8 @@ Outputs
                                  primary HDU) as float32 + their parameters
   tests/golden/examples.npz      input data of examples/*.ini (C1-C3): images,
                                  PSFs, gain/offset, object lists, prior ranges
+  tests/golden/objects/          the reference's objects/*.cl, byte for byte (test
+                                 input: the plugin files a Lensed user has)
   tests/golden/ref_outputs.npz   (only if oracle/_ref is built) outputs of the
                                  reference's own kernels compiled on the host for
                                  the named configurations -- the parity vectors
@@ -113,8 +115,25 @@ def examples():
     print("examples.npz", list(meta))
 
 
+def reference_objects():
+    """The reference's objects/*.cl, verbatim, as the plugin directory every GPU
+    test, smoke() and bench.py run on (tests/golden/objects/README.md)."""
+    import hashlib
+    import shutil
+    dst = os.path.join(OUT, "objects")
+    os.makedirs(dst, exist_ok=True)
+    sums = []
+    for path in sorted(glob.glob(os.path.join(REF, "objects", "*.cl"))):
+        shutil.copyfile(path, os.path.join(dst, os.path.basename(path)))
+        sums.append(f"{hashlib.sha256(open(path, 'rb').read()).hexdigest()}  {os.path.basename(path)}\n")
+    shutil.copyfile(os.path.join(REF, "LICENSE.txt"), os.path.join(dst, "LICENSE.txt"))
+    open(os.path.join(dst, "SHA256SUMS"), "w").writelines(sums)
+    print("objects/", len(sums), "files")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    reference_objects()
     quad_rules()
     ref_goldens()
     examples()

@@ -68,7 +68,7 @@ def main():
         print(f"{fn:10s} {packed}")
 
     print("\n## executed PTX instructions per pair of rays of the C5 scene (interpreter, 20 random pairs, fast build)")
-    ctx = L.Context(device=-1)
+    ctx = L.Context(device=-1, objects_dir=os.path.join(ROOT, "tests", "golden", "objects"))
     cfg = H.synthetic_config("c5", 64)
     flags = L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH
     src, block = TR._program(cfg, ctx, flags)
@@ -102,7 +102,7 @@ def main():
     img = np.zeros((w["height"], w["width"]), np.float32)
     for tag, env in (("off", ""), ("on ", "-DLCU_PF_LIBM_PAIR=1")):
         os.environ["LCU_NVRTC_FLAGS"] = env
-        m = L.Model(L.Context(device=-1), w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=flags)
+        m = L.Model(L.Context(device=-1, objects_dir=os.path.join(ROOT, "tests", "golden", "objects")), w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=flags)
         print(tag, m.kernel_usage("lcu_render_pair"))
     os.environ.pop("LCU_NVRTC_FLAGS", None)
 

@@ -17,6 +17,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJECTS_DIR = os.path.join(ROOT, "tests", "golden", "objects")      # the reference's objects/*.cl, verbatim
 sys.path.insert(0, ROOT)
 
 import lensed_b200 as L                                     # noqa: E402
@@ -72,7 +73,7 @@ def main():
     ap.add_argument("--out", default=None, help="root for MultiNest-layout result files")
     args = ap.parse_args()
 
-    ctx = L.Context(device=0)
+    ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
     flags = 0 if args.math == "strict" else (L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
     cfg, model, like = build(ctx, args.name, flags)
     rng = np.random.default_rng(0)
