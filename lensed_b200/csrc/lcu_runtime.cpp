@@ -238,14 +238,24 @@ size_t group_count(const lcu_model* m)
     return div_up((r1 - r0)*m->width, 32);
 }
 
-int ensure_partial(lcu_model* m)
+// chi^2 partial sums of up to nb points per launch ([nb][groups] doubles): sized
+// by the largest batch actually launched, not by maxb (a 4096^2 model without a
+// PSF has 524288 groups per point: 4 MB per point)
+int ensure_partial(lcu_model* m, size_t nb)
 {
-    const size_t need = m->maxb*group_count(m);
+    nb = std::min(std::max<size_t>(nb, 1), m->maxb);
+    const size_t need = nb*group_count(m);
     if(need <= m->partial_cap)
         return LCU_OK;
+    if(m->graph1)
+    {
+        cudaGraphExecDestroy(m->graph1);    // the graph refers to the old buffer
+        m->graph1 = nullptr;
+    }
     if(m->d_partial)
         cudaFree(m->d_partial);
     m->d_partial = nullptr;
+    m->partial_cap = 0;
     RT_CHECK(cudaMalloc(&m->d_partial, need*sizeof(double)));
     m->partial_cap = need;
     return LCU_OK;
@@ -467,7 +477,7 @@ void harvest_profile(lcu_model* m)
 
 int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_lnew, cudaStream_t st)
 {
-    int rc = ensure_partial(m);
+    int rc = ensure_partial(m, std::min(m->maxb, nbatch));
     if(rc) return rc;
     rc = ensure_raw(m, std::min(m->maxb, nbatch));
     if(rc) return rc;
@@ -514,7 +524,7 @@ bool single_point_graph(lcu_model* m)
         cudaGraphExecDestroy(m->graph1);
         m->graph1 = nullptr;
     }
-    if(getenv("LCU_NO_GRAPH") || ensure_partial(m) != LCU_OK || ensure_raw(m, 1) != LCU_OK)
+    if(getenv("LCU_NO_GRAPH") || ensure_partial(m, 1) != LCU_OK || ensure_raw(m, 1) != LCU_OK)
     {
         m->graph1_off = true;
         return false;
@@ -872,13 +882,23 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     // in HBM (budget LCU_RAW_BUDGET_MB, default 4096)
     {
         const size_t used = m->nq*16 + m->psfw*m->psfh*4 + 2048;
-        size_t maxb = used < 65536 ? (65536 - used)/(m->words*4) : 1;
-        maxb = std::min<size_t>(std::max<size_t>(maxb, 1), 1024);
-        if(m->has_psf)
+        if(used + m->words*4 > 65536)
         {
+            // lcu_quad + lcu_psf + one object block have to fit the 64 KB constant bank
+            set_error("lcu_model_create: quadrature rule (%zu points), PSF (%zu x %zu) and object block (%zu words) need %zu bytes "
+                      "of constant memory, more than the 64 KB bank holds", m->nq, m->psfw, m->psfh, m->words, used + m->words*4);
+            delete m;
+            return LCU_E_ARG;
+        }
+        size_t maxb = (65536 - used)/(std::max<size_t>(m->words, 1)*4);
+        maxb = std::min<size_t>(std::max<size_t>(maxb, 1), 1024);
+        {
+            // per point and launch: the staged pre-PSF image (PSF models) and one double per 32 pixels
+            // of chi^2 partial sums; budget LCU_RAW_BUDGET_MB (default 4096) for the sum of the two
             const char* env = getenv("LCU_RAW_BUDGET_MB");
             const size_t budget = (env && *env ? (size_t)atoll(env) : 4096) << 20;
-            maxb = std::min(maxb, std::max<size_t>(budget/(m->size*sizeof(float)), 1));
+            const size_t per_point = (m->has_psf ? m->size*sizeof(float) : 0) + div_up(m->size, 32)*sizeof(double);
+            maxb = std::min(maxb, std::max<size_t>(budget/std::max<size_t>(per_point, 1), 1));
         }
         if(desc->max_batch)
             maxb = std::min(maxb, desc->max_batch);
@@ -1061,7 +1081,7 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(RT_CHECK(cudaMemset(m->d_counter, 0, m->maxb*sizeof(unsigned))));
     for(cudaEvent_t& e : m->ev_io)
         M_CHECK(RT_CHECK(cudaEventCreate(&e)));
-    M_CHECK(return ensure_partial(m));
+    M_CHECK(return ensure_partial(m, 1));
     M_CHECK(return ensure_stage(m, 64));
 #undef M_CHECK
 
@@ -1306,7 +1326,7 @@ int lcu_render(lcu_model* m, const float* params, float* model_img, float* raw, 
     RT_CHECK(cudaSetDevice(m->ctx->device));
     rc = ensure_stage(m, 1);
     if(rc) return rc;
-    rc = ensure_partial(m);
+    rc = ensure_partial(m, 1);
     if(rc) return rc;
     const size_t bytes = m->size*sizeof(float);
     float** bufs[] = { &m->d_value1, &m->d_error1, &m->d_model1, &m->d_chi1 };

@@ -103,7 +103,7 @@ def read_image(spec: str, dtype=np.float32):
     section = None
     ext = None
     for b in brackets:
-        if re.match(r"^\s*-?\*?\s*$|^[\d\s:,*-]+$", b) and ":" in b:
+        if re.match(r"^[\d\s:,*-]+$", b) and ("," in b):
             section = b
         else:
             ext = b
@@ -115,14 +115,43 @@ def read_image(spec: str, dtype=np.float32):
         hdr, data = next((h, d) for h, d in hdus if str(h.get("EXTNAME", "")).upper() == ext.strip().upper())
     if data is None or data.ndim != 2:
         raise ValueError(f"{spec}: no 2-D image")
-    rx, ry = 1.0, 1.0
+    rx, ry, sx, sy = 1.0, 1.0, 1.0, 1.0
     if section:
-        xs, ys = section.split(",")
-        x0, x1 = (int(v) for v in xs.split(":"))
-        y0, y1 = (int(v) for v in ys.split(":"))
-        data = data[y0 - 1:y1, x0 - 1:x1]
-        rx, ry = float(x0), float(y0)
-    return np.ascontiguousarray(data, dtype=dtype), (rx, ry, 1.0, 1.0)
+        axes = section.split(",")
+        if len(axes) != 2:
+            raise ValueError(f"{spec}: image section must have two axes")
+        (x0, x1, xi), (y0, y1, yi) = (_section_range(spec, a) for a in axes)
+        data = data[_section_slice(y0, y1, yi), _section_slice(x0, x1, xi)]
+        # src/data.c:262-270: origin = first pixel of the section, scale = +-increment
+        rx, sx = float(x0), float(xi if x1 > x0 else -xi)
+        ry, sy = float(y0), float(yi if y1 > y0 else -yi)
+    return np.ascontiguousarray(data, dtype=dtype), (rx, ry, sx, sy)
+
+
+def _section_range(spec: str, text: str):
+    """`first:last[:increment]` of one axis of a CFITSIO image section
+    (1-based, inclusive; first > last reverses the axis).  The `*` / `-*`
+    shorthands are rejected: the reference derives its pixel origin from the
+    section's first pixel (src/data.c:262-270), which CFITSIO leaves unset for them."""
+    parts = [t.strip() for t in text.split(":")]
+    if any("*" in t for t in parts):
+        raise ValueError(f"{spec}: '*' in an image section is not supported, write the pixel range out (first:last)")
+    try:
+        vals = [int(t) for t in parts]
+    except ValueError:
+        raise ValueError(f"{spec}: bad image section '{text}'") from None
+    if len(vals) == 2:
+        vals.append(1)
+    if len(vals) != 3 or vals[0] < 1 or vals[1] < 1 or vals[2] < 1:
+        raise ValueError(f"{spec}: bad image section '{text}'")
+    return tuple(vals)
+
+
+def _section_slice(first: int, last: int, inc: int):
+    if last >= first:
+        return slice(first - 1, last, inc)
+    stop = last - 2
+    return slice(first - 1, stop if stop >= 0 else None, -inc)
 
 
 def _card(key: str, value, comment: str = "") -> bytes:
@@ -141,29 +170,35 @@ def _card(key: str, value, comment: str = "") -> bytes:
     return f"{s:<80}"[:80].encode("ascii")
 
 
-def write_layers(path: str, layers, names):
-    """Write float32 image layers as primary HDU + IMAGE extensions, the
-    structure of the reference's results file (src/data.c:129-165)."""
+def _header(cards) -> bytes:
+    hdr = b"".join(cards + [f"{'END':<80}".encode("ascii")])
+    return hdr + b" " * (-len(hdr) % _BLOCK)
+
+
+def write_layers(path: str, layers, names, empty_primary: bool = True):
+    """Write float32 image layers in the structure of the reference's results
+    file (write_fits, src/data.c:129-165): an empty primary HDU (16-bit, no
+    axes) carrying ORIGIN and DATE, then one IMAGE extension per layer with its
+    EXTNAME -- so IMG is HDU 1 and PVL HDU 6 of a results file, as for the
+    reference.  empty_primary=False puts the first layer into the primary HDU
+    instead (a plain image file)."""
+    import datetime
     out = bytearray()
+    if empty_primary:
+        out += _header([_card("SIMPLE", True, "conforms to FITS standard"), _card("BITPIX", 16), _card("NAXIS", 0),
+                        _card("EXTEND", True), _card("ORIGIN", "lensed-b200", "FITS file originator"),
+                        _card("DATE", datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%M:%S"),
+                              "file creation date (YYYY-MM-DDThh:mm:ss UT)")])
     for idx, (img, name) in enumerate(zip(layers, names)):
         img = np.asarray(img, dtype=np.float32)
         h, w = img.shape
-        cards = []
-        if idx == 0:
-            cards.append(_card("SIMPLE", True, "conforms to FITS standard"))
-        else:
-            cards.append(_card("XTENSION", "IMAGE", "IMAGE extension"))
+        primary = idx == 0 and not empty_primary
+        cards = [_card("SIMPLE", True, "conforms to FITS standard") if primary else _card("XTENSION", "IMAGE", "IMAGE extension")]
         cards += [_card("BITPIX", -32), _card("NAXIS", 2), _card("NAXIS1", w), _card("NAXIS2", h)]
-        if idx == 0:
-            cards.append(_card("EXTEND", True))
-        else:
-            cards += [_card("PCOUNT", 0), _card("GCOUNT", 1)]
-        cards.append(_card("EXTNAME", name))
-        cards.append(f"{'END':<80}".encode("ascii"))
-        hdr = b"".join(cards)
-        hdr += b" " * (-len(hdr) % _BLOCK)
+        cards += [_card("EXTEND", True)] if primary else [_card("PCOUNT", 0), _card("GCOUNT", 1)]
+        cards.append(_card("EXTNAME", name, "extension name"))
         data = img.astype(">f4").tobytes()
         data += b"\0" * (-len(data) % _BLOCK)
-        out += hdr + data
+        out += _header(cards) + data
     with open(path, "wb") as f:
         f.write(bytes(out))

@@ -358,7 +358,8 @@ def build(path: str, ctx: Context, **model_kw):
 
     image, pcs = fits.read_image(rel(opt["image"]))
     if "bscale" in opt:
-        image = (image*np.float32(float(opt["bscale"]))).astype(np.float32)
+        # image[i] *= bscale with a double bscale (src/lensed.c:430): widen, multiply, narrow once
+        image = (image.astype(np.float64)*float(opt["bscale"])).astype(np.float32)
 
     def value_or_file(v):
         try:
@@ -423,15 +424,28 @@ def find_mode(values, mask=None, bins: int = 100):
 # ---------------------------------------------------------------------------
 # dumper
 # ---------------------------------------------------------------------------
-def dumper_layers(model: Model, params, image, weight) -> dict:
-    """The six result layers of src/nested.c:219-253 for one parameter point."""
-    out = model.render(params)
-    img = out["model"]
+def layers_from_maps(model_img, raw, error, chi, image, weight) -> dict:
+    """The host-side arithmetic of the dumper (src/nested.c:219-253) on the four
+    maps it reads back from the device: RES = image - model (float), ERR =
+    error/value (float division; 0/0 and x/0 are NaN / inf as in the
+    reference), PVL = erfc(sqrt(0.5 chi^2)) evaluated in double and narrowed."""
+    img = np.asarray(model_img, np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
-        relerr = (out["error"]/out["raw"]).astype(np.float32)
-    pvl = np.array([math.erfc(math.sqrt(0.5*c)) for c in out["chi"].ravel().tolist()], np.float32).reshape(img.shape)
-    return {"IMG": img, "RES": (np.asarray(image, np.float32) - img).astype(np.float32), "RAW": out["raw"], "ERR": relerr,
-            "WHT": np.asarray(weight, np.float32), "PVL": pvl}
+        relerr = (np.asarray(error, np.float32)/np.asarray(raw, np.float32)).astype(np.float32)
+    half = 0.5*np.asarray(chi, np.float32).astype(np.float64)
+    pvl = np.array([math.erfc(math.sqrt(c)) if c >= 0 else math.nan for c in half.ravel().tolist()], np.float32).reshape(img.shape)
+    return {"IMG": img, "RES": (np.asarray(image, np.float32) - img).astype(np.float32), "RAW": np.asarray(raw, np.float32),
+            "ERR": relerr, "WHT": np.asarray(weight, np.float32), "PVL": pvl}
+
+
+def dumper_layers(model: Model, params, image, weight) -> dict:
+    """The six result layers of src/nested.c:178-253 for one parameter point:
+    re-render on the device (lcu_render), layer arithmetic on the host as in the
+    reference.  (The reference's PVL layer shows the chi^2 map of the last point
+    MultiNest evaluated -- its dumper does not re-run the loglike kernel; here it
+    is the map of the point given.)"""
+    out = model.render(params)
+    return layers_from_maps(out["model"], out["raw"], out["error"], out["chi"], image, weight)
 
 
 def write_results(path: str, layers: dict):

@@ -923,6 +923,38 @@ int orc_loglike(orc_model* m, const float* params, double* lnew, real* model_out
     return 0;
 }
 
+/* the dumper's six result layers, src/nested.c:178-253: re-render the given
+ * point (set_params, render, convolve: :187-205), then on the host
+ *   IMG = the model image (convolved if there is a PSF, :208)
+ *   RES = image - IMG                                   (:223-224)
+ *   RAW = the rendered value image                      (:240)
+ *   ERR = error / value, the relative quadrature error  (:230-231)
+ *   WHT = the weight map                                (:242)
+ *   PVL = erfc(sqrt(0.5*loglike))                       (:237-238; a float times the
+ *         double constant 0.5: evaluated in double and narrowed on assignment)
+ * all as float arrays.  The reference's dumper does not re-run its loglike
+ * kernel, so its PVL layer shows the chi^2 map of the point MultiNest evaluated
+ * last; here the map is that of the point passed in (what the reference shows
+ * when the last sampled point is the maximum-likelihood one). */
+int orc_dumper_layers(orc_model* m, const float* params, float* img, float* res, float* raw, float* err, float* wht, float* pvl)
+{
+    double lnew;
+    size_t k;
+    const real* model;
+    orc_loglike(m, params, &lnew, NULL, NULL);
+    model = m->psf ? m->conv : m->value;
+    for(k = 0; k < m->size; ++k)
+    {
+        img[k] = (float)model[k];
+        res[k] = (float)(m->image[k] - model[k]);
+        raw[k] = (float)m->value[k];
+        err[k] = (float)(m->error[k]/m->value[k]);
+        wht[k] = (float)m->weight[k];
+        pvl[k] = (float)erfc(sqrt(0.5*(double)m->chi[k]));
+    }
+    return 0;
+}
+
 /* data preparation helpers used to build fixtures the way the reference's
  * host does: weight map src/data.c:314-330, PSF normalisation :354-370 */
 void orc_make_weight(const float* image, const float* gain, double offset, size_t n, float* weight)

@@ -62,6 +62,8 @@ def lib(variant: str = "strict"):
     L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_convolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_loglike.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    if hasattr(L, "orc_dumper_layers"):
+        L.orc_dumper_layers.argtypes = [C.c_void_p]*8
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_max_threads.restype = C.c_int
     L.orc_make_weight.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_size_t, C.c_void_p]
@@ -173,6 +175,15 @@ class Model:
         out = np.zeros_like(a)
         if self.L.orc_convolve(self.h, _ptr(a), _ptr(out)):
             raise ValueError("model has no PSF")
+        return out
+
+    def dumper_layers(self, params):
+        """The six result layers of the reference's dumper (src/nested.c:219-253), float32."""
+        p = _f32(params)
+        assert p.size == self.npars
+        names = ("IMG", "RES", "RAW", "ERR", "WHT", "PVL")
+        out = {n: np.zeros((self.height, self.width), np.float32) for n in names}
+        self.L.orc_dumper_layers(self.h, _ptr(p), *[_ptr(out[n]) for n in names])
         return out
 
     def loglike(self, params, want_maps=False):

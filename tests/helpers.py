@@ -119,6 +119,15 @@ def synthetic_config(which: str, size: int, psf: bool = True, psf_shape=None, ma
     return cfg
 
 
+def c5_fixture_observation(model512):
+    """(image, weight) of the full-size C5 fixture (tools/make_c5_fixture.py):
+    the committed 512^2 oracle model block-replicated 8 x 8 and divided by 64
+    (exact in float32) plus seeded noise; no renderer involved, so every
+    machine rebuilds the same bits (the fixture carries a SHA-256 to prove it)."""
+    m = np.kron(np.asarray(model512, np.float32), np.ones((8, 8), np.float32))*np.float32(1.0/64)
+    return workloads.observe(m, 12346)
+
+
 def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)

@@ -136,3 +136,18 @@ static void set(global data* this, float x, float y, float r, float w, float amp
     img = np.zeros((8, 8), np.float32)
     m = L.Model(ctx, ["ring"], img, img)
     assert "brightness_ring" in m.source and m.npars == 5
+
+
+def test_constant_bank_budget_is_checked(compile_ctx):
+    """Quadrature table + PSF + object block have to fit the 64 KB constant
+    bank: a rule that cannot is a clean LCU_E_ARG with the sizes in the message,
+    not an NVRTC / ptxas failure."""
+    img = np.zeros((8, 8), np.float32)
+    n = 4100
+    qq = np.zeros((n, 2), np.float32)
+    ww = np.full((n, 2), 1.0/n, np.float32)
+    with pytest.raises(L.LensedCudaError, match="constant memory"):
+        L.Model(compile_ctx, ["sersic"], img, img, qq=qq, ww=ww)
+    # a large but admissible rule still builds
+    m = L.Model(compile_ctx, ["sersic"], img, img, qq=qq[:1024], ww=ww[:1024])
+    assert m.nq == 1024 and m.max_batch >= 1

@@ -26,26 +26,73 @@ FAST = 4 | 32
 MATH_MODES = [pytest.param(0, id="strict"), pytest.param(FAST, id="fast")]
 
 
-def _lnew_tol(cfg, lnew, base=LOGLIKE_TOL):
-    """Relative tolerance for one log-likelihood: 1e-6 wherever the model
-    fits (chi^2/dof < 10, the region a sampler resolves).  At badly fitting
-    points (the 1 %-off batch: chi^2/dof ~ 10^2) the residuals are dominated by
-    model mismatch, per-pixel rounding differences add up coherently, and the
-    strict float32 oracle itself is 0.6e-6 ... 4.2e-6 away from its float64
-    twin and 1.4e-6 ... 2.4e-6 from the reference's code built with its own
-    fast-math flags: 4e-6 there."""
-    chi2_dof = -2*lnew/cfg.image.size
-    return base if chi2_dof < 10 else max(base, 4e-6)
+# ---------------------------------------------------------------------------
+# Parity criteria.  Two are evaluated and RECORDED for every case (the record
+# goes to gpurun_out/parity_report.json; a copy per round is committed under
+# profiles/):
+#
+#   flat   the north-star's letter: per-pixel |gpu - o32|/|o32| <= 1e-5,
+#          |lnew_gpu - lnew_o32|/|lnew_o32| <= 1e-6, o32 = the strict-float32 oracle;
+#   floor  |gpu - f64| <= 1.5 |o32 - f64|: the CUDA path is no further from the
+#          exact (float64) answer than the reference's own float32 arithmetic is.
+#          Two independent float32 evaluations of an ill-conditioned scene
+#          cannot agree better than either agrees with the exact result.  For a
+#          scalar (lnew) one float32 realisation may land on the float64 value
+#          by luck, so the floor there is the largest distance from float64 among
+#          the float32 realisations at hand: the strict oracle, its -ffast-math
+#          build (what -cl-fast-relaxed-math licenses the reference's compiler to
+#          do, src/lensed.c:744-748) and the reference's own kernels where built.
+#
+# The 99.9th percentile of the per-pixel error has to meet the flat bound
+# always.  The maximum and lnew have to meet the flat bound wherever a test
+# says flat=True (the reference's 16 configurations, C1-C3, the C4 scenes, every
+# truth point from 256^2 up) and flat-or-floor elsewhere (random ill-conditioned
+# scenes, 1 %-off points with chi^2/dof ~ 10^2, pre-PSF C5).
+# ---------------------------------------------------------------------------
+FLOOR_K = 1.5
+_REPORT = []
 
 
-def _check_images(out, cfg, om):
+@pytest.fixture(scope="module", autouse=True)
+def _parity_report():
+    yield
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "parity_report.json"), "w") as f:
+            json.dump(_REPORT, f, indent=0)
+    except OSError:
+        pass
+
+
+def _check_lnew(cfg, params, got, flat=False, tag="", om=None):
+    """One log-likelihood against the oracle: flat 1e-6, or the floor criterion."""
+    om = om or cfg.oracle()
+    l32 = om.loglike(params)
+    l64 = cfg.oracle(variant="f64").loglike(params)
+    others = {"fast": cfg.oracle(variant="fast").loglike(params)}
+    floor = max([abs(l32 - l64)] + [abs(v - l64) for v in others.values()])
+    n = cfg.image.size
+    rec = dict(case=cfg.name, what="lnew", tag=tag, gpu=got, o32=l32, f64=l64, rel_vs_o32=abs(got - l32)/abs(l32),
+               rel_vs_f64=abs(got - l64)/abs(l64), floor_rel=floor/abs(l64), chi2_per_pixel=-2*l64/n,
+               flat_ok=bool(abs(got - l32) <= LOGLIKE_TOL*abs(l32)), floor_ok=bool(abs(got - l64) <= FLOOR_K*floor),
+               flat_required=flat)
+    _REPORT.append(rec)
+    if flat:
+        assert rec["flat_ok"], f"{cfg.name} {tag}: lnew {got} vs {l32} (rel {rec['rel_vs_o32']:.3e})"
+    else:
+        assert rec["flat_ok"] or rec["floor_ok"], \
+            f"{cfg.name} {tag}: lnew {got} vs o32 {l32} (rel {rec['rel_vs_o32']:.3e}), vs f64 {rec['rel_vs_f64']:.3e}, floor {rec['floor_rel']:.3e}"
+    return l32
+
+
+def _check_images(out, cfg, om, flat=False, tag=""):
     """Per-pixel relative error of the raw (pre-PSF) and model images against
-    the strict-float32 oracle.  Bound: PIXEL_TOL = 1e-5 at the 99.9th
-    percentile always, and for the maximum as well unless the oracle's own
-    float32 rounding noise on this scene (its distance from its float64 twin)
-    is already that large -- two independent float32 evaluations cannot agree
-    better than either agrees with the exact result -- in which case the
-    maximum may reach 1.5x that noise floor."""
+    the strict-float32 oracle: p99.9 <= 1e-5 always; the maximum <= 1e-5
+    (flat=True), or else no further from the float64 twin than 1.5 x the
+    oracle's own maximum distance from it."""
     value, error = om.render(cfg.params)
     lnew, model, chi = om.loglike(cfg.params, want_maps=True)
     o64 = cfg.oracle(variant="f64")
@@ -54,11 +101,20 @@ def _check_images(out, cfg, om):
     stats = {}
     for key, ref, ref64 in (("raw", value, v64), ("model", model, m64)):
         r = H.rel_err(out[key], ref)
-        floor = H.rel_err(ref, ref64).max()
-        tol = max(PIXEL_TOL, 1.5*floor)
-        stats[key] = (r.max(), floor)
-        assert np.quantile(r, 0.999) <= PIXEL_TOL, f"{cfg.name}: {key} image p99.9 rel err {np.quantile(r, 0.999):.3e}"
-        assert r.max() <= tol, f"{cfg.name}: {key} image max rel err {r.max():.3e} (f32 noise floor {floor:.3e})"
+        fl = H.rel_err(ref, ref64)
+        r64 = H.rel_err(out[key], ref64)
+        rec = dict(case=cfg.name, what=key, tag=tag, max=float(r.max()), p999=float(np.quantile(r, 0.999)),
+                   floor_max=float(fl.max()), floor_p999=float(np.quantile(fl, 0.999)), gpu_vs_f64_max=float(r64.max()),
+                   flat_ok=bool(r.max() <= PIXEL_TOL), floor_ok=bool(r64.max() <= FLOOR_K*fl.max()),
+                   flat_required=bool(flat is True or (flat and key in flat)))
+        _REPORT.append(rec)
+        stats[key] = (r.max(), fl.max())
+        assert rec["p999"] <= PIXEL_TOL, f"{cfg.name}: {key} image p99.9 rel err {rec['p999']:.3e}"
+        if flat is True or (flat and key in flat):
+            assert rec["flat_ok"], f"{cfg.name}: {key} image max rel err {r.max():.3e}"
+        else:
+            assert rec["flat_ok"] or rec["floor_ok"], \
+                f"{cfg.name}: {key} image max rel err {r.max():.3e} vs o32, {r64.max():.3e} vs f64 (f32 noise floor {fl.max():.3e})"
     # the quadrature error estimate is a sum with alternating-sign weights:
     # compare it on the scale of the value it estimates the error of
     scale = np.maximum(np.abs(value), 1e-30)
@@ -89,7 +145,7 @@ def test_reference_known_answer_configs(gpu_ctx, name, flags):
     om = cfg.oracle()
     m = cfg.product(gpu_ctx, flags=flags)
     out = m.render(cfg.params)
-    lnew, _ = _check_images(out, cfg, om)
+    lnew, _ = _check_images(out, cfg, om, flat=True, tag=f"flags={flags}")
     # loose anchor against the reference's golden image: chi^2/dof << 1
     got = m.loglike(cfg.params)
     n = cfg.image.size
@@ -110,9 +166,8 @@ def test_examples(gpu_ctx, name, ipp, flags):
     om = cfg.oracle()
     m = cfg.product(gpu_ctx, flags=flags)
     out = m.render(cfg.params)
-    lnew, _ = _check_images(out, cfg, om)
-    got = m.loglike(cfg.params)
-    assert abs(got - lnew) <= LOGLIKE_TOL*abs(lnew), f"{cfg.name}: lnew {got} vs {lnew}"
+    _check_images(out, cfg, om, flat=True, tag=f"flags={flags}")
+    _check_lnew(cfg, cfg.params, m.loglike(cfg.params), flat=True, tag=f"flags={flags}", om=om)
     _check_block(m, om, cfg)
     # per-pixel chi^2 map (PVL layer of the dumper)
     _, _, chi = om.loglike(cfg.params, want_maps=True)
@@ -124,33 +179,30 @@ def test_examples(gpu_ctx, name, ipp, flags):
                                             ("c4", 256, True)])
 def test_synthetic_scenes(gpu_ctx, which, size, psf, flags):
     """Scaled C4 / C5 scenes on noisy images (chi^2 ~ N_pix: well-conditioned
-    lnew).  The relative error of lnew that per-pixel rounding noise eps causes
-    scales like 2 (S/N) eps / sqrt(N_pix): 1e-6 is the bar from 256^2 pixels
-    up (the named configurations are 1024^2 and 4096^2); the 128^2 scenes are
-    held to 3e-6."""
-    tol = LOGLIKE_TOL if size >= 256 else 3*LOGLIKE_TOL
+    lnew).  Images: flat 1e-5 (the pre-PSF image of the EPL scene, whose oracle
+    is itself 1e-5 from its float64 twin, by the floor criterion).  lnew at the
+    truth: flat 1e-6 from 256^2 pixels up (rounding noise eps moves lnew by
+    ~2 (S/N) eps / sqrt(N_pix); the named configurations are 1024^2 and 4096^2),
+    flat-or-floor at 128^2 and at the 1 %-off points of the batch (chi^2/dof ~
+    10^2: per-pixel differences add up coherently with the residuals)."""
     cfg = H.synthetic_config(which, size, psf=psf)
     om = cfg.oracle()
     m = cfg.product(gpu_ctx, flags=flags)
     out = m.render(cfg.params)
-    lnew, _ = _check_images(out, cfg, om)
-    got = m.loglike(cfg.params)
-    assert abs(got - lnew) <= tol*abs(lnew), f"{cfg.name}: lnew {got} vs {lnew}"
+    _check_images(out, cfg, om, flat=True if which == "c4" else {"model"}, tag=f"flags={flags}")
+    _check_lnew(cfg, cfg.params, m.loglike(cfg.params), flat=size >= 256, tag=f"truth flags={flags}", om=om)
     # batch of perturbed points (1 % off the truth: chi^2/dof ~ 10^2)
     P = H.workloads.param_batch(cfg.extra["workload"], 5)
-    ref = np.array([om.loglike(p) for p in P])
     got = m.loglike_batch(P)
-    tols = np.array([_lnew_tol(cfg, r, tol) for r in ref])
-    rel = np.abs(got - ref)/np.abs(ref)
-    assert np.all(rel <= tols), f"{cfg.name}: batch lnew rel err {rel} (tolerances {tols})"
+    for i, p in enumerate(P):
+        _check_lnew(cfg, p, got[i], flat=False, tag=f"batch[{i}] flags={flags}", om=om)
 
 
 def test_masked_pixels(gpu_ctx):
     cfg = H.synthetic_config("c4", 128, mask=0.1)
     assert (cfg.weight == 0).mean() > 0.05
     om, m = cfg.oracle(), cfg.product(gpu_ctx)
-    lnew = om.loglike(cfg.params)
-    assert abs(m.loglike(cfg.params) - lnew) <= LOGLIKE_TOL*abs(lnew)
+    _check_lnew(cfg, cfg.params, m.loglike(cfg.params), flat=True, tag="masked", om=om)
 
 
 @pytest.mark.parametrize("psf_shape", [(9, 9), (8, 8), (6, 11), (25, 25), (1, 1)])
@@ -317,8 +369,8 @@ def test_empty_and_ragged_batches(gpu_ctx):
     assert m.loglike_batch(np.zeros((0, m.npars), np.float32)).shape == (0,)
     P = H.workloads.param_batch(cfg.extra["workload"], 11)          # 4 + 4 + 3
     got = m.loglike_batch(P)
-    ref = np.array([cfg.oracle().loglike(p) for p in P])
-    assert np.all(np.abs(got - ref) <= 3*LOGLIKE_TOL*np.abs(ref))
+    for i, p in enumerate(P):
+        _check_lnew(cfg, p, got[i], flat=False, tag=f"ragged[{i}]")
     with pytest.raises(ValueError):
         m.loglike_batch(np.zeros((3, m.npars + 1), np.float32))
 
@@ -351,6 +403,66 @@ def test_full_size_c5_properties(gpu_ctx):
     r = H.rel_err(raw[2032:2064], value)
     floor = H.rel_err(value, v64).max()
     assert np.quantile(r, 0.999) <= PIXEL_TOL and r.max() <= max(PIXEL_TOL, 1.5*floor), f"{r.max():.3e} floor {floor:.3e}"
+
+
+@pytest.mark.parametrize("flags", MATH_MODES)
+def test_full_size_c5_loglike_against_reference_fixture(gpu_ctx, flags):
+    """lnew of C5 at its full 4096^2 (822 M rays per evaluation) at the truth and
+    at two perturbed points against the committed answers of the reference's own
+    kernels compiled on the host (oracle/_ref) and of the oracle port in float32
+    and float64 (tests/golden/c5_4096_lnew.npz, tools/make_c5_fixture.py).  The
+    observed image is rebuilt here from the committed 512^2 model without any
+    renderer in the loop; its SHA-256 proves both sides saw the same pixels."""
+    import hashlib
+    import os
+    path = os.path.join(H.GOLDEN, "c5_4096_lnew.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c5_4096_lnew.npz not generated")
+    z = np.load(path)
+    image, weight = H.c5_fixture_observation(z["model512"])
+    if hashlib.sha256(image.tobytes()).hexdigest() != str(z["image_sha256"]) or \
+            hashlib.sha256(weight.tobytes()).hexdigest() != str(z["weight_sha256"]):
+        pytest.skip("this machine's numpy draws a different noise realisation than the fixture's: nothing to compare")
+    w = H.workloads.c5(4096)
+    m = H.Config("C5-4096-fixture", w["objects"], w["truth"], image, weight, rule=w["rule"], psf=w["psf"]).product(gpu_ctx, flags=flags)
+    P = z["params"]
+    got = m.loglike_batch(P)
+    assert got[0] == m.loglike(P[0])
+    ref = z["lnew_ref"] if "lnew_ref" in z else z["lnew_strict"]
+    l64 = z["lnew_f64"]
+    for i in range(len(P)):
+        floor = max(abs(z[k][i] - l64[i]) for k in ("lnew_ref", "lnew_strict") if k in z)
+        rec = dict(case="C5-4096-fixture", what="lnew", tag=f"point {i} flags={flags}", gpu=float(got[i]), o32=float(ref[i]),
+                   f64=float(l64[i]), rel_vs_o32=abs(got[i] - ref[i])/abs(ref[i]), rel_vs_f64=abs(got[i] - l64[i])/abs(l64[i]),
+                   floor_rel=floor/abs(l64[i]), chi2_per_pixel=-2*l64[i]/image.size,
+                   flat_ok=bool(abs(got[i] - ref[i]) <= LOGLIKE_TOL*abs(ref[i])), floor_ok=bool(abs(got[i] - l64[i]) <= FLOOR_K*floor),
+                   flat_required=i == 0)
+        _REPORT.append(rec)
+        assert rec["flat_ok"] or (i > 0 and rec["floor_ok"]), rec
+
+
+@pytest.mark.parametrize("name", ["test_sersic_bulge", "full_mock_psf", "full_mock_nopsf"])
+def test_dumper_layers_against_oracle(gpu_ctx, name):
+    """The six result layers of the dumper (src/nested.c:178-253) for C1 / C3 / C2
+    from lcu_render + the host arithmetic, against the oracle's restatement:
+    IMG and RAW to the image bound, RES = image - IMG exactly, WHT exactly, ERR
+    (a ratio of a cancelling sum to the value) on the scale of the value, PVL
+    absolutely (it is a probability)."""
+    from lensed_b200 import host
+    cfg = H.example_config(name)
+    om, m = cfg.oracle(), cfg.product(gpu_ctx)
+    ref = om.dumper_layers(cfg.params)
+    got = host.dumper_layers(m, cfg.params, cfg.image, cfg.weight)
+    assert set(got) == set(ref) == {"IMG", "RES", "RAW", "ERR", "WHT", "PVL"}
+    for k in ("IMG", "RAW"):
+        assert H.rel_err(got[k], ref[k]).max() <= PIXEL_TOL, k
+    assert np.array_equal(got["RES"], cfg.image - got["IMG"]) and np.array_equal(got["WHT"], ref["WHT"])
+    assert np.abs(got["RES"] - ref["RES"]).max() <= PIXEL_TOL*np.abs(ref["IMG"]).max()
+    # ERR = error/value: the error estimate is a sum with alternating-sign weights, accurate to ~1e-5 of the value
+    assert np.nanmax(np.abs(got["ERR"].astype(np.float64) - ref["ERR"])) <= 10*PIXEL_TOL
+    # PVL = erfc(sqrt(chi^2/2)): d/dchi^2 is bounded by 1/sqrt(2 pi chi^2); compare absolutely
+    assert np.abs(got["PVL"].astype(np.float64) - ref["PVL"]).max() <= 1e-4
+    assert np.all((got["PVL"] >= 0) & (got["PVL"] <= 1))
 
 
 def test_single_point_graph_and_profile(gpu_ctx, monkeypatch):
@@ -441,20 +553,17 @@ def test_every_object_in_one_model(gpu_ctx, flags):
     m = cfg.product(gpu_ctx, flags=flags)
     assert m.npars == params.size and m.words == 12 + 4 + 16 + 4 + 4 + 12*4
     out = m.render(params)
-    lnew, _ = _check_images(out, cfg, om)
-    got = m.loglike(params)
-    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew)          # 60^2 pixels
+    _check_images(out, cfg, om, tag=f"flags={flags}")
+    _check_lnew(cfg, params, m.loglike(params), flat=False, tag=f"flags={flags}", om=om)          # 60^2 pixels
     _check_block(m, om, cfg)
 
 
-# seeds 0 ... 23 of helpers.random_config whose scene is well conditioned in
-# float32, screened on the CPU: the strict oracle is within 3.6e-6 of its
-# float64 twin at the 99.9th percentile (seeds 0, 1, 6, 7, 18, 22 are 5e-6 ...
-# 9e-6 from it, which leaves no room under the 1e-5 bound), and no pixel moves by
-# more than 1e-5 when sin / cos results change by one ulp (tools/libm_sensitivity.py;
-# seed 20 has one pixel on a critical curve of its epl_plus_shear lens that moves
-# by 1.6e-5 -- the CUDA path is 1.5e-5 from the oracle there, 1.5e-6 at p99.9)
-RANDOM_SEEDS = [2, 3, 4, 5, 8, 9, 11, 12, 13, 14, 15, 16, 17, 19, 21, 23]
+# all 24 seeds of helpers.random_config, the ill-conditioned ones included (seeds
+# 0, 1, 6, 7, 18, 22: the strict oracle is itself 5e-6 ... 9e-6 from its float64
+# twin at the 99.9th percentile; seed 20 has a pixel on a critical curve of its
+# epl_plus_shear lens that moves by 1.6e-5 when sin / cos change by one ulp,
+# tools/libm_sensitivity.py): held to flat-or-floor, both recorded
+RANDOM_SEEDS = list(range(24))
 
 
 @pytest.mark.parametrize("flags", MATH_MODES)
@@ -468,9 +577,9 @@ def test_random_models(gpu_ctx, seed, flags):
     om = cfg.oracle()
     m = cfg.product(gpu_ctx, flags=flags)
     out = m.render(cfg.params)
-    lnew, _ = _check_images(out, cfg, om)
+    _check_images(out, cfg, om, tag=f"flags={flags}")
     got = m.loglike(cfg.params)
-    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew), f"{cfg.name} {cfg.objects}: lnew {got} vs {lnew}"
+    _check_lnew(cfg, cfg.params, got, flat=False, tag=f"flags={flags}", om=om)
     _check_block(m, om, cfg, atol=1e-6)
     P = np.stack([cfg.params, cfg.params*np.float32(1.0005)])
     assert np.array_equal(m.loglike_batch(P)[0], got)
@@ -494,10 +603,8 @@ def test_random_models_with_image_plane_priors(gpu_ctx, seed):
     m = cfg.product(gpu_ctx, flags=FAST)
     _check_block(m, om, cfg, atol=1e-6)
     out = m.render(cfg.params)
-    _check_images(out, cfg, om)
-    lnew = om.loglike(cfg.params)
-    got = m.loglike(cfg.params)
-    assert abs(got - lnew) <= 3*LOGLIKE_TOL*abs(lnew), f"{cfg.name}: lnew {got} vs {lnew}"
+    _check_images(out, cfg, om, tag="ipp")
+    _check_lnew(cfg, cfg.params, m.loglike(cfg.params), flat=False, tag="ipp", om=om)
 
 
 def test_pixel_coordinate_system(gpu_ctx):

@@ -189,8 +189,10 @@ def test_reference_style_known_answer_run(gpu_ctx, tmp_path):
     assert np.allclose(layers["RES"], ref.image - layers["IMG"]) and np.all((layers["PVL"] >= 0) & (layers["PVL"] <= 1))
     host.write_results(str(tmp_path / "out.fits"), layers)
     back = fits.read_hdus(str(tmp_path / "out.fits"))
-    assert [h["EXTNAME"] for h, _ in back] == ["IMG", "RES", "RAW", "ERR", "WHT", "PVL"]
-    assert np.array_equal(back[0][1], layers["IMG"])
+    # 7 HDUs as the reference writes them: empty primary, then IMG = HDU 1 ... PVL = HDU 6 (src/data.c:129-165)
+    assert len(back) == 7 and back[0][1] is None
+    assert [h["EXTNAME"] for h, _ in back[1:]] == ["IMG", "RES", "RAW", "ERR", "WHT", "PVL"]
+    assert np.array_equal(back[1][1], layers["IMG"])
 
 
 def test_find_mode_and_mask(compile_ctx, tmp_path):

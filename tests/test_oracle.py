@@ -59,6 +59,33 @@ def test_port_equals_reference_kernels_bit_for_bit():
         lb, mb, cb = b.loglike(cfg.params, want_maps=True)
         assert np.array_equal(ma.view(np.uint32), mb.view(np.uint32)) and np.array_equal(ca.view(np.uint32), cb.view(np.uint32))
         assert la == lb, cfg.name
+        # the dumper's six layers (src/nested.c:219-253): RES, ERR = error/value, PVL = erfc(sqrt(chi^2/2)) included
+        da, db = a.dumper_layers(cfg.params), b.dumper_layers(cfg.params)
+        for k in ("IMG", "RES", "RAW", "ERR", "WHT", "PVL"):
+            assert np.array_equal(da[k].view(np.uint32), db[k].view(np.uint32)), (cfg.name, k)
+
+
+def test_dumper_layers_restated():
+    """The dumper arithmetic on its own terms (src/nested.c:219-253), and the
+    product's host-side copy of it (lensed_b200.host.layers_from_maps) fed with
+    the oracle's maps: the same bits in all six layers."""
+    from lensed_b200 import host
+    for cfg in (H.example_config("test_sersic_bulge"), H.example_config("full_mock_psf"), H.synthetic_config("c4", 64, psf=False)):
+        om = cfg.oracle()
+        d = om.dumper_layers(cfg.params)
+        value, error = om.render(cfg.params)
+        _, model, chi = om.loglike(cfg.params, want_maps=True)
+        assert np.array_equal(d["IMG"], model) and np.array_equal(d["RAW"], value) and np.array_equal(d["WHT"], cfg.weight)
+        assert np.array_equal(d["RES"], cfg.image - model)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            assert np.array_equal(d["ERR"], error/value, equal_nan=True)
+        assert np.all((d["PVL"] >= 0) & (d["PVL"] <= 1))
+        k = int(np.argmax(chi))
+        import math
+        assert d["PVL"].ravel()[k] == np.float32(math.erfc(math.sqrt(0.5*float(chi.ravel()[k]))))
+        mine = host.layers_from_maps(model, value, error, chi, cfg.image, cfg.weight)
+        for name in d:
+            assert np.array_equal(mine[name].view(np.uint32), d[name].view(np.uint32)), (cfg.name, name)
 
 
 @pytest.mark.skipif(not O.available("ref"), reason="oracle/_ref not built (needs the reference tree)")
