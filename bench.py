@@ -136,8 +136,11 @@ def describe(w):
 # ---------------------------------------------------------------------------
 CPU_KINDS = (
     # variant of oracle/pyoracle, kind, description
-    ("ref_simd", "reference", "the reference's objects/*.cl and generated compute()/set_params() compiled on the host with "
-                              "float = 8 consecutive work-items (AVX2 lanes), -O3 -ffast-math, OpenMP over rows: "
+    ("ref_simd512", "reference", "the reference's objects/*.cl and generated compute() compiled on the host with float = 16 "
+                                 "consecutive work-items (AVX-512 lanes, libmvec), -O3 -ffast-math, OpenMP over work-groups: "
+                                 "what a vectorising OpenCL CPU runtime does with them"),
+    ("ref_simd", "reference", "the reference's objects/*.cl and generated compute() compiled on the host with float = 8 "
+                              "consecutive work-items (AVX2 lanes, libmvec), -O3 -ffast-math, OpenMP over work-groups: "
                               "what a vectorising OpenCL CPU runtime does with them"),
     ("ref_fast", "reference", "the reference's kernels compiled on the host one scalar work-item at a time, -O3 -ffast-math, "
                               "OpenMP over pixels"),

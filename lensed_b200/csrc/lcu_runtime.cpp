@@ -1009,6 +1009,24 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
                 m->log = log2;
             }
         }
+        // The other way round: a ray function that needs 65 ... 80 registers fits
+        // 3 blocks per SM (24 warps); if ptxas can do it in 64 at the price of a few
+        // spilled words outside the hot path, 4 blocks fit (32 warps).  Measured on
+        // C5 (epl_plus_shear + 3 sersic: 76 -> 64 registers, stack 32 -> 48 bytes):
+        // +2.9 % (profiles/r02_call2_summary.txt); building for 5 blocks gains nothing.
+        else if(!(extra && strstr(extra, "LCU_PAIR_MINBLOCKS")) && regs > 64 && regs <= 80)
+        {
+            const std::string src4 = assemble(4);
+            std::vector<char> cubin4;
+            std::string log4;
+            if(ctx->compile(src4, m->flags, &cubin4, &log4) && cubin_kernel_usage(cubin4, "lcu_render_pair", &regs2, &stack2)
+               && regs2 <= 64 && stack2 <= stack + 32)
+            {
+                m->source = src4;
+                m->cubin.swap(cubin4);
+                m->log = log4;
+            }
+        }
     }
 
     if(ctx->device < 0)

@@ -21,6 +21,14 @@ Pipeline
      -O2 -ffp-contract=off) and liblensed_ref_fast.so (-O3 -ffast-math, AVX2,
      OpenMP; the timed CPU baseline, kind "reference").
 
+  5. the same plugin text a second way, for timing only: per-ray functions and
+     the generated compute() with float = 8 consecutive work-items (AVX2 lanes,
+     oracle/ref_shim_simd.h), uniform data kept scalar, render / convolve /
+     loglike driven over work-groups > 1 (ref_driver.cpp -DREF_SIMD) ->
+     liblensed_ref_simd.so (AVX2, 8 lanes) and liblensed_ref_simd512.so (AVX-512,
+     16 lanes; used where the CPU has it): what a vectorising OpenCL CPU runtime (the Intel
+     runtime of .travis.yml:60-68) makes of the reference's kernels.
+
 The only transformation applied to reference text is the token rewrite of
 OpenCL vector literals "(float2)(a, b)" -> "float2(a, b)" (a cast of a comma
 expression in C++), and -fpermissive for the implicit void* conversions of the
@@ -56,6 +64,119 @@ def rewrite(text):
 
 def ident(name):
     return re.sub(r"[^A-Za-z0-9_]", "_", name)
+
+
+def strip_comments(text):
+    text = re.sub(r"/\*.*?\*/", lambda m: re.sub(r"[^\n]", " ", m.group(0)), text, flags=re.S)
+    return re.sub(r"//[^\n]*", "", text)
+
+
+def match_brace(text, i):
+    """index just past the brace that closes the one at text[i]"""
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return j + 1
+    raise ValueError("unbalanced braces")
+
+
+def object_parts(name):
+    """(data block, per-ray text) of an object file: `data { ... };` as written,
+    and the file with type / params / data / set() blanked out -- what is left is
+    the deflection / brightness / foreground function (and any helpers)."""
+    text = strip_comments(open(os.path.join(REF, "objects", name + ".cl")).read())
+    out = text
+    data_block = None
+    for key in ("type", "params", "data"):
+        m = re.search(r"(?m)^\s*%s\b" % key, out)
+        if not m:
+            continue
+        if key == "type":
+            end = out.index(";", m.start()) + 1
+        else:
+            end = match_brace(out, out.index("{", m.start()))
+            end = out.index(";", end) + 1
+        if key == "data":
+            data_block = out[m.start():end]
+        out = out[:m.start()] + out[end:]
+    m = re.search(r"static\s+void\s+set\s*\(", out)
+    if m:
+        end = match_brace(out, out.index("{", m.start()))
+        out = out[:m.start()] + out[end:]
+    if data_block is None:
+        raise ValueError(f"{name}: no data block")
+    return data_block, out
+
+
+def compute_text(main_text):
+    """the generated compute() of a main program (src/kernel.c:65-111)"""
+    i = main_text.index("static float compute(")
+    return main_text[i:match_brace(main_text, main_text.index("{", i))]
+
+
+SELECT = re.compile(r"dot\(a,\s*a\) < HUGE_VALF \? a : float2\(1E10f, 1E10f\)")
+
+
+def simd_unit(ci, cfg, main_text):
+    """Translation unit of one configuration for the SIMD build: scalar data
+    structs, then the per-ray functions and compute() with float = vfloat, then
+    the render loop of kernel/lensed.cl:9-38 over 8 work-items at a time."""
+    kdir = os.path.join(REF, "kernel")
+    names = list(dict.fromkeys(cfg["objects"]))
+    o = ['#include "ref_shim.h"\n#include "ref_shim_simd.h"\n', f"namespace simd_cfg_{ci} {{\n"]
+    o.append(rewrite(open(os.path.join(kdir, "object.cl")).read()))
+    o.append(rewrite(open(os.path.join(kdir, "constants.cl")).read()))
+    parts = {n: object_parts(n) for n in names}
+    for n in names:
+        o.append(f"#define data struct data_{ident(n)}\n{rewrite(parts[n][0])}\n#undef data\n")
+    o.append("#define float vfloat\n#define float2 vfloat2\n#define float4 vfloat4\n#define mat22 vfloat4\n")
+    for n in names:
+        o.append(f"#define data struct data_{ident(n)}\n")
+        for fn in ("deflection", "brightness", "foreground"):
+            o.append(f"#define {fn} {fn}_{ident(n)}\n")
+        o.append(rewrite(parts[n][1]) + "\n")
+        o.append("#undef data\n#undef deflection\n#undef brightness\n#undef foreground\n")
+    comp, nsub = SELECT.subn("ref_select(dot(a,a) < HUGE_VALF, a, float2(1E10f, 1E10f))", rewrite(compute_text(main_text)))
+    if "deflection_" in comp and nsub == 0:
+        raise ValueError("generated compute(): deflection guard not found")
+    o.append(comp + "\n")
+    o.append("#undef float\n#undef float2\n#undef float4\n#undef mat22\n")
+    o.append("""
+static void render8(const uint* data, const float* pcs, const ::float2* qq, const ::float2* ww, int nq,
+                    long k0, long k1, long size, int width, float* value, float* error)
+{
+    for(long k = k0; k < k1; k += REF_LANES)
+    {
+        vfloat px, py;
+        for(int l = 0; l < REF_LANES; ++l)
+        {
+            const long kk = k + l < size ? k + l : size - 1;
+            px.v[l] = (float)(kk % width);
+            py.v[l] = (float)(kk / width);
+        }
+        const vfloat2 x(vfloat(pcs[0]) + vfloat(pcs[2])*px, vfloat(pcs[1]) + vfloat(pcs[3])*py);
+        vfloat f0 = 0.0f, f1 = 0.0f;
+        for(int n = 0; n < nq; ++n)
+        {
+            const vfloat c = compute((uint*)data, x + qq[n]);
+            f0 += vfloat(ww[n].x)*c;
+            f1 += vfloat(ww[n].y)*c;
+        }
+        for(int l = 0; l < REF_LANES && k + l < k1; ++l)
+        {
+            value[k + l] = f0.v[l];
+            error[k + l] = f1.v[l];
+        }
+    }
+}
+""")
+    o.append("}\n#undef kernel\n#undef global\n#undef local\n#undef constant\n#undef this\n")
+    o.append(f"extern const ref_simd_render_fn REF_SIMD_RENDER_{ci} = simd_cfg_{ci}::render8;\n")
+    return "".join(o)
 
 
 def main():
@@ -133,13 +254,19 @@ def main():
         # 3. main programs
         configs = json.load(open(os.path.join(HERE, "ref_configs.json")))
         cfg_units = []
+        simd_units = []
         for ci, cfg in enumerate(configs):
             specs = []
             for name, ipp in zip(cfg["objects"], cfg["ipp"]):
                 m = metas[name]
                 ipp = (ipp or "").ljust(m["npars"], "0") if m["npars"] else "0"
                 specs.append(f"{name}:{m['type']}:{m['words']}:{m['npars']}:{ipp}:{m['ptypes'] or '0'}")
-            text = rewrite(gen("main", *specs))
+            main_raw = gen("main", *specs)
+            text = rewrite(main_raw)
+            spath = os.path.join(tmp, f"simd_{ci}.cpp")
+            with open(spath, "w") as f:
+                f.write(simd_unit(ci, cfg, main_raw))
+            simd_units.append(spath)
             path = os.path.join(tmp, f"cfg_{ci}.cpp")
             with open(path, "w") as f:
                 f.write('#include "ref_shim.h"\n')
@@ -174,9 +301,32 @@ def main():
             run([CC, "-std=c99", "-O2", "-fPIC", "-w", "-I", os.path.join(tmp, "stubinc"), "-I", src, "-c", cfile, "-o", o])
             quad_objs.append(o)
         units = [os.path.join(HERE, "ref_driver.cpp"), table, ctable, *meta_units, *cfg_units]
-        run([CXX, *strict, "-shared", "-o", os.path.join(OUT, "liblensed_ref.so"), *units, *quad_objs, "-lm"])
+        from concurrent.futures import ThreadPoolExecutor
+
+        def compile_link(name, flags, srcs, libs=()):
+            """one object file per unit, compiled in parallel, then linked into oracle/_ref/<name>"""
+            tag = os.path.splitext(name)[0]
+            objs = [os.path.join(tmp, f"{tag}_{i}.o") for i in range(len(srcs))]
+            print(f"+ {CXX} {' '.join(flags[:5])} ... -> {name} ({len(srcs)} units, {os.cpu_count()} jobs)", flush=True)
+            with ThreadPoolExecutor(os.cpu_count() or 1) as pool:
+                list(pool.map(lambda so: subprocess.run([CXX, *flags, "-c", so[0], "-o", so[1]], check=True), zip(srcs, objs)))
+            run([CXX, "-shared", "-fopenmp", "-o", os.path.join(OUT, name), *objs, *quad_objs, *libs, "-lm"])
+        compile_link("liblensed_ref.so", strict, units)
         fast = ["-std=gnu++17", "-O3", "-march=x86-64-v3", "-ffast-math", "-fpermissive", "-w", "-fPIC", "-fopenmp", "-I", HERE]
-        run([CXX, *fast, "-shared", "-o", os.path.join(OUT, "liblensed_ref_fast.so"), *units, *quad_objs, "-lm"])
+        compile_link("liblensed_ref_fast.so", fast, units)
+        # 5. the vectorised build (timing only)
+        stable = os.path.join(tmp, "simd_table.cpp")
+        with open(stable, "w") as f:
+            f.write('#include "ref_shim.h"\n#include "ref_shim_simd.h"\n#undef kernel\n#undef global\n#undef local\n#undef constant\n#undef this\n')
+            for ci in range(len(configs)):
+                f.write(f"extern const ref_simd_render_fn REF_SIMD_RENDER_{ci};\n")
+            f.write("extern const ref_simd_render_fn REF_SIMD_RENDER[] = {\n")
+            f.write("".join(f"    REF_SIMD_RENDER_{ci},\n" for ci in range(len(configs))))
+            f.write("};\n")
+        for tag, lanes, march in (("simd", 8, "x86-64-v3"), ("simd512", 16, "x86-64-v4")):
+            flags = ["-std=gnu++17", "-O3", f"-march={march}", "-ffast-math", "-fpermissive", "-w", "-fPIC", "-fopenmp",
+                     "-I", HERE, f"-DREF_SIMD={lanes}"]
+            compile_link(f"liblensed_ref_{tag}.so", flags, [*units, stable, *simd_units], libs=["-lmvec"])
         json.dump(dict(objects=metas, skipped=skipped, configs=configs), open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
         print("built", os.listdir(OUT))
     finally:

@@ -26,12 +26,28 @@ _VARIANTS = {
     "ref_fast": os.path.join("_ref", "liblensed_ref_fast.so"),
     # the same reference text with float = 8 consecutive work-items (AVX2): timing only
     "ref_simd": os.path.join("_ref", "liblensed_ref_simd.so"),
+    "ref_simd512": os.path.join("_ref", "liblensed_ref_simd512.so"),
 }
 
 _libs: dict = {}
 
 
+def _cpu_has(flag: str) -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return flag in line.split()
+    except OSError:
+        pass
+    return False
+
+
 def available(variant: str = "strict") -> bool:
+    if variant == "ref_simd512" and not _cpu_has("avx512f"):
+        return False
+    if variant == "ref_simd" and not _cpu_has("avx2"):
+        return False
     return os.path.exists(os.path.join(HERE, _VARIANTS[variant]))
 
 

@@ -24,6 +24,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#ifdef REF_SIMD
+#include <immintrin.h>        /* ref_shim_simd.h; system headers must precede the qualifier macros below */
+#endif
 
 /* OpenCL math built-ins are overloaded on float: make the unqualified calls in
  * the reference text pick the float overloads, not C's double functions */
