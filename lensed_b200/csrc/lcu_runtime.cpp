@@ -116,6 +116,7 @@ struct RenderArgs
     float pcs[4];
     long long k0, nk;
     const uint32_t* objs;
+    const float* params;
     float* value;
     float* error;
     const float* image;
@@ -168,6 +169,7 @@ struct lcu_model
     CUmodule mod = nullptr;
     CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_conv_small = nullptr, f_reduce = nullptr;
     CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
+    CUfunction f_render_fold[4] = {};                                   // split kernels with set_params folded in
     CUfunction f_make_weight = nullptr;
     bool pair = false;
     CUdeviceptr c_objs = 0;
@@ -335,7 +337,19 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
     if(reduced) *reduced = false;
     const bool may_fuse = want_chi2 && reduce_out && reduced && !getenv("LCU_NO_FUSED_REDUCE");
     if(ev) cudaEventRecord(ev[0], st);
+    size_t r0, r1;
+    render_rows(m, &r0, &r1);
+    const size_t nk = (r1 - r0)*m->width;
+    const int ngroups = (int)group_count(m);
+    const int split = pick_split(m, nk, nb);
+    // Small launches (one to four points of a small image: the sampler's
+    // one-point-per-call pattern): the split render kernels run set_params
+    // themselves, once per block, which takes one kernel and one dependency out
+    // of the launch sequence (lcu_set_params_block: the same code, the same bits).
+    // LCU_NO_FOLD_SETTER keeps the separate kernel.
+    const bool fold = split > 1 && nb <= 4 && !error && !getenv("LCU_NO_FOLD_SETTER");
     // set_params, src/nested.c:77
+    if(!fold)
     {
         int B = (int)nb;
         void* args[] = { &B, (void*)&d_params, &m->d_objs };
@@ -343,11 +357,6 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         if(rc) return rc;
     }
 
-    size_t r0, r1;
-    render_rows(m, &r0, &r1);
-    const size_t nk = (r1 - r0)*m->width;
-    const int ngroups = (int)group_count(m);
-    const int split = pick_split(m, nk, nb);
     // the large-image kernels read the object blocks from the constant bank;
     // the split kernels (small images) take them from global memory themselves
     if(m->obj_const && split == 1)
@@ -362,6 +371,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
         a.k0 = (long long)(r0*m->width);
         a.nk = (long long)nk;
         a.objs = m->d_objs;
+        a.params = fold ? d_params : nullptr;
         a.value = m->has_psf ? (value ? value : m->d_raw) : value;
         a.error = error;
         a.image = m->d_image;
@@ -391,8 +401,8 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
             rc = launch(m, a.error ? m->f_render_pair_err : m->f_render_pair, dim3((unsigned)div_up(nk, 512), (unsigned)nb),
                         dim3(256), args, st);
         else
-            rc = launch(m, a.error ? m->f_render_err[idx] : m->f_render[idx], dim3((unsigned)div_up(nk, 256/split), (unsigned)nb),
-                        dim3(256), args, st);
+            rc = launch(m, a.error ? m->f_render_err[idx] : fold ? m->f_render_fold[idx] : m->f_render[idx],
+                        dim3((unsigned)div_up(nk, 256/split), (unsigned)nb), dim3(256), args, st);
         if(rc) return rc;
     }
     if(ev) cudaEventRecord(ev[2], st);
@@ -1047,6 +1057,9 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[1], m->mod, "lcu_render_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[2], m->mod, "lcu_render_s4")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[3], m->mod, "lcu_render_s8")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[1], m->mod, "lcu_render_fold_s2")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[2], m->mod, "lcu_render_fold_s4")));
+    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[3], m->mod, "lcu_render_fold_s8")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[0], m->mod, "lcu_render_err_s1")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[1], m->mod, "lcu_render_err_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[2], m->mod, "lcu_render_err_s4")));

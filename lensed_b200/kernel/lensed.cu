@@ -65,6 +65,8 @@ struct lcu_render_args
     long long k0;           // first pixel of the rendered range
     long long nk;           // number of pixels in the range
     const uint* objs;       // [B][LCU_WORDS]
+    const float* params;    // [B][LCU_NPARS]: read by the lcu_render_fold_s* kernels, which run set_params
+                            // themselves (one thread per block) instead of reading objs
     float* value;           // [B][IMAGE_SIZE] or null
     float* error;           // [B][IMAGE_SIZE] or null
     const float* image;     // [IMAGE_SIZE]
@@ -97,6 +99,24 @@ lcu_set_params(int B, const float* __restrict__ params, uint* __restrict__ objs)
 #pragma unroll
     for(int i = 0; i < LCU_WORDS/4; ++i)
         out[i] = make_uint4(blk[4*i], blk[4*i+1], blk[4*i+2], blk[4*i+3]);
+}
+
+// set_params inside a render block (small launches: the single-point latency
+// path).  Every block of a point computes the point's object block itself, in one
+// thread, with exactly the code of lcu_set_params -- the same bits, redundantly
+// -- which takes the set_params kernel and the dependency on it out of the
+// launch sequence.  Not inlined: the double-precision setter code must not cost
+// the ray loop registers.
+__device__ __noinline__ void lcu_set_params_block(uint* sdata, const float* __restrict__ params)
+{
+    __align__(16) uint blk[LCU_WORDS];
+#pragma unroll
+    for(int i = 0; i < LCU_WORDS; ++i)
+        blk[i] = 0;
+    lcu_set_params_body(blk, params);
+#pragma unroll
+    for(int i = 0; i < LCU_WORDS; ++i)
+        sdata[i] = blk[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -154,7 +174,8 @@ __device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsig
 
 // ERR: also accumulate the quadrature error estimate (second weight); only
 // the dumper asks for it, the likelihood path does not pay for it
-template<int S, bool ERR>
+// FOLD: the block computes its point's object block itself (lcu_set_params_block)
+template<int S, bool ERR, bool FOLD = false>
 __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 {
     constexpr int P = LCU_BLOCK/S;          // pixels per block
@@ -181,8 +202,16 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 #endif
     {
         __shared__ __align__(16) uint sdata[LCU_WORDS];
-        for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
-            sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
+        if constexpr(FOLD)
+        {
+            if(threadIdx.x == 0)
+                lcu_set_params_block(sdata, a.params + (size_t)b*LCU_NPARS);
+        }
+        else
+        {
+            for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+                sdata[i] = a.objs[(size_t)b*LCU_WORDS + i];
+        }
         __syncthreads();
         data = sdata;
     }
@@ -320,6 +349,14 @@ LCU_RENDER_KERNEL(1)
 LCU_RENDER_KERNEL(2)
 LCU_RENDER_KERNEL(4)
 LCU_RENDER_KERNEL(8)
+
+// the split kernels with set_params folded in (small launches, likelihood path only)
+#define LCU_RENDER_FOLD_KERNEL(S) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
+    lcu_render_fold_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, false, true>(a); }
+LCU_RENDER_FOLD_KERNEL(2)
+LCU_RENDER_FOLD_KERNEL(4)
+LCU_RENDER_FOLD_KERNEL(8)
 
 #if LCU_PAIR
 // Two rays per thread (shim.cuh: packed pairs).  A warp covers 64 consecutive

@@ -504,9 +504,30 @@ def test_single_point_graph_and_profile(gpu_ctx, monkeypatch):
     the per-stage profile must account for every evaluation."""
     import lensed_b200 as L
     cfg = H.example_config("full_mock_psf")
-    m = cfg.product(gpu_ctx)
     P = np.stack([cfg.params*(1 + 1e-3*i) for i in range(4)]).astype(np.float32)
+    big = np.repeat(P, 8, axis=0)                            # 32 points: the batched path with its own set_params kernel
+    # default: small launches run set_params inside the render blocks -- two kernels per point
+    # (render + set_params, convolve + reduction), one without a PSF -- and give the bits of the batched path
+    mf = cfg.product(gpu_ctx)
+    ref = mf.loglike_batch(big)[::8]
+    n0 = L.launch_count()
+    assert np.array_equal(np.array([mf.loglike(p) for p in P]), ref)
+    assert L.launch_count() - n0 == 4*2
+    assert np.array_equal(mf.loglike_batch(P), ref)          # four points: folded as well
+    mf.close()
+    cfg0 = H.example_config("full_mock_nopsf")
+    P0 = np.stack([cfg0.params*(1 + 1e-3*i) for i in range(4)]).astype(np.float32)
+    mf0 = cfg0.product(gpu_ctx)
+    ref0 = mf0.loglike_batch(np.repeat(P0, 8, axis=0))[::8]
+    n0 = L.launch_count()
+    assert np.array_equal(np.array([mf0.loglike(p) for p in P0]), ref0)
+    assert L.launch_count() - n0 == 4*1
+    mf0.close()
+    # the rest of this test: the separate set_params kernel (LCU_NO_FOLD_SETTER), same bits
+    monkeypatch.setenv("LCU_NO_FOLD_SETTER", "1")
+    m = cfg.product(gpu_ctx)
     batch = m.loglike_batch(P)
+    assert np.array_equal(batch, ref)
     n0 = L.launch_count()
     single = np.array([m.loglike(p) for p in P])           # graph path
     assert np.array_equal(single, batch)

@@ -15,11 +15,13 @@ ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
     cfg = H.example_config(name)
     res = {}
-    for mode in ("graph", "plain"):
+    for mode in ("graph", "graph_separate_set_params", "plain"):
+        for env in ("LCU_NO_GRAPH", "LCU_NO_FOLD_SETTER"):
+            os.environ.pop(env, None)
         if mode == "plain":
             os.environ["LCU_NO_GRAPH"] = "1"
-        else:
-            os.environ.pop("LCU_NO_GRAPH", None)
+        elif mode == "graph_separate_set_params":
+            os.environ["LCU_NO_FOLD_SETTER"] = "1"
         m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
         for _ in range(20):
             v = m.loglike(cfg.params)
@@ -30,9 +32,14 @@ for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
         dt = (time.perf_counter() - t0)/n
         res[mode] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, lnew=v)
         m.close()
-    assert res["graph"]["lnew"] == res["plain"]["lnew"]
+    assert res["graph"]["lnew"] == res["plain"]["lnew"] == res["graph_separate_set_params"]["lnew"]
+    for env in ("LCU_NO_GRAPH", "LCU_NO_FOLD_SETTER"):
+        os.environ.pop(env, None)
     try:
-        om = cfg.oracle(variant="ref_fast")
+        from oracle import pyoracle as O
+        variant = next(v for v in ("ref_simd512", "ref_simd", "ref_fast") if O.available(v))
+        om = cfg.oracle(variant=variant, lib=O.lib(variant))
+        res["cpu_build"] = variant
         om.loglike(cfg.params)
         n = 200
         t0 = time.perf_counter()
