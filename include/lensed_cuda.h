@@ -224,6 +224,18 @@ int lcu_model_get_weight(lcu_model* model, float* weight);
  */
 int lcu_loglike(lcu_model* model, const float* params, double* lnew);
 
+/* lcu_loglike in two halves, for a host that has work of its own between
+ * proposing a point and needing its likelihood (the prior transform of the next
+ * point, src/nested.c:43-61; book-keeping of the sampler): lcu_loglike_async
+ * copies the parameters, starts the evaluation and returns a ticket at once;
+ * lcu_loglike_wait returns the ticket's log-likelihood (src/nested.c:115).  Up
+ * to two evaluations may be in flight (they run one after the other on the
+ * model's stream; the second is queued while the first runs); a third
+ * lcu_loglike_async, and any other evaluation call on the model, fails with
+ * LCU_E_ARG until one of them has been waited for.  Same bits as lcu_loglike. */
+int lcu_loglike_async(lcu_model* model, const float* params, int* ticket);
+int lcu_loglike_wait(lcu_model* model, int ticket, double* lnew);
+
 /* Batched entry point: B independent parameter points per call,
  * params[B][npars] -> lnew[B], host memory. */
 int lcu_loglike_batch(lcu_model* model, size_t nbatch, const float* params, double* lnew);

@@ -77,6 +77,8 @@ SYMBOLS = {
     "lcu_model_make_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_void_p]),
     "lcu_model_get_weight": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lcu_loglike": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "lcu_loglike_async": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "lcu_loglike_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "lcu_loglike_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "lcu_loglike_batch_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lcu_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

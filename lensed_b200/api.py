@@ -264,6 +264,18 @@ class Model:
         check(lib.lcu_loglike(self._h, _ptr(p), C.byref(v)))
         return v.value
 
+    def loglike_async(self, params) -> int:
+        """Start one evaluation and return its ticket (at most two in flight)."""
+        p = self._params(params, False)
+        t = C.c_int()
+        check(lib.lcu_loglike_async(self._h, _ptr(p), C.byref(t)))
+        return t.value
+
+    def loglike_wait(self, ticket: int) -> float:
+        v = C.c_double()
+        check(lib.lcu_loglike_wait(self._h, int(ticket), C.byref(v)))
+        return v.value
+
     def loglike_batch(self, params) -> np.ndarray:
         p = self._params(params, True)
         out = np.zeros(p.shape[0], np.float64)

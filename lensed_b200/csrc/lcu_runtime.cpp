@@ -188,6 +188,10 @@ struct lcu_model
     // single-point evaluation (the sampler's one-point callback) as a CUDA graph:
     // upload, 3-4 kernels, constant-bank copy and read-back replayed by one launch
     cudaGraphExec_t graph1 = nullptr;
+    cudaGraphExec_t graph1b = nullptr;  // the same graph on the second staging slot (lcu_loglike_async)
+    int async_next = 0;                 // slot the next lcu_loglike_async takes
+    bool async_busy[2] = { false, false };
+    cudaEvent_t async_done[2] = { nullptr, nullptr };   // completion of a slot's evaluation when it is not watched
     bool graph1_off = false;
     size_t graph1_rows[2] = { 0, 0 };
     int graph1_split = 0, graph1_conv = -1;
@@ -205,6 +209,15 @@ struct lcu_model
 };
 
 namespace {
+
+// the single-point graphs refer to the staging / scratch buffers: drop them before any of those moves
+void drop_point_graphs(lcu_model* m)
+{
+    if(m->graph1) cudaGraphExecDestroy(m->graph1);
+    if(m->graph1b) cudaGraphExecDestroy(m->graph1b);
+    m->graph1 = nullptr;
+    m->graph1b = nullptr;
+}
 
 int launch(lcu_model* m, CUfunction f, dim3 grid, dim3 block, void** args, cudaStream_t stream)
 {
@@ -249,11 +262,7 @@ int ensure_partial(lcu_model* m, size_t nb)
     const size_t need = nb*group_count(m);
     if(need <= m->partial_cap)
         return LCU_OK;
-    if(m->graph1)
-    {
-        cudaGraphExecDestroy(m->graph1);    // the graph refers to the old buffer
-        m->graph1 = nullptr;
-    }
+    drop_point_graphs(m);                   // the graphs refer to the old buffer
     if(m->d_partial)
         cudaFree(m->d_partial);
     m->d_partial = nullptr;
@@ -268,11 +277,7 @@ int ensure_raw(lcu_model* m, size_t nb)
 {
     if(!m->has_psf || nb <= m->raw_cap)
         return LCU_OK;
-    if(m->graph1)
-    {
-        cudaGraphExecDestroy(m->graph1);    // the graph refers to the old buffer
-        m->graph1 = nullptr;
-    }
+    drop_point_graphs(m);                   // the graphs refer to the old buffer
     if(m->d_raw)
         cudaFree(m->d_raw);
     m->d_raw = nullptr;
@@ -286,12 +291,7 @@ int ensure_stage(lcu_model* m, size_t nbatch)
 {
     if(nbatch <= m->stage_cap)
         return LCU_OK;
-    if(m->graph1)
-    {
-        // the single-point graph refers to the staging buffers
-        cudaGraphExecDestroy(m->graph1);
-        m->graph1 = nullptr;
-    }
+    drop_point_graphs(m);                   // the single-point graphs refer to the staging buffers
     if(m->d_params) cudaFree(m->d_params);
     if(m->d_lnew) cudaFree(m->d_lnew);
     if(m->h_params) cudaFreeHost(m->h_params);
@@ -342,12 +342,13 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
     const size_t nk = (r1 - r0)*m->width;
     const int ngroups = (int)group_count(m);
     const int split = pick_split(m, nk, nb);
-    // Small launches (one to four points of a small image: the sampler's
-    // one-point-per-call pattern): the split render kernels run set_params
-    // themselves, once per block, which takes one kernel and one dependency out
-    // of the launch sequence (lcu_set_params_block: the same code, the same bits).
-    // LCU_NO_FOLD_SETTER keeps the separate kernel.
-    const bool fold = split > 1 && nb <= 4 && !error && !getenv("LCU_NO_FOLD_SETTER");
+    // Opt-in (LCU_FOLD_SETTER=1): for small launches (one to four points of a small
+    // image) the split render kernels run set_params themselves, once per block, which
+    // takes one kernel and one dependency out of the launch sequence
+    // (lcu_set_params_block: the same code, the same bits).  Measured slower than the
+    // separate kernel, hence not the default.
+    const char* fold_env = getenv("LCU_FOLD_SETTER");
+    const bool fold = split > 1 && nb <= 4 && !error && fold_env && *fold_env == '1';
     // set_params, src/nested.c:77
     if(!fold)
     {
@@ -529,57 +530,58 @@ bool single_point_graph(lcu_model* m)
     if(m->graph1 && m->graph1_rows[0] == m->row0 && m->graph1_rows[1] == m->row1 && m->graph1_split == split
        && m->graph1_conv == conv)
         return true;
-    if(m->graph1)
-    {
-        cudaGraphExecDestroy(m->graph1);
-        m->graph1 = nullptr;
-    }
+    drop_point_graphs(m);
     if(getenv("LCU_NO_GRAPH") || ensure_partial(m, 1) != LCU_OK || ensure_raw(m, 1) != LCU_OK)
     {
         m->graph1_off = true;
         return false;
     }
-    cudaGraph_t graph = nullptr;
-    const unsigned long long launches0 = g_launches.load();
-    bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    // one graph per staging slot: slot 0 serves lcu_loglike, both serve lcu_loglike_async
     bool mapped = false;
-    if(ok)
+    for(int slot = 0; slot < 2; ++slot)
     {
-        // The pinned staging buffers are mapped into the device's address space
-        // (unified addressing): set_params reads the point's few parameters straight
-        // from host memory and the reduction writes the result there, which takes
-        // the two copy nodes (and their dependencies) out of the graph.  LCU_GRAPH_COPIES
-        // restores them.
-        float* dp = nullptr;
-        double* dl = nullptr;
-        mapped = !getenv("LCU_GRAPH_COPIES")
-            && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), m->h_params, 0) == cudaSuccess
-            && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dl), m->h_lnew, 0) == cudaSuccess && dp && dl;
-        if(!mapped)
-            cudaGetLastError();
-        if(mapped)
-            ok = enqueue_batch(m, 1, dp, dl, m->stream) == LCU_OK;
-        else
+        cudaGraph_t graph = nullptr;
+        const unsigned long long launches0 = g_launches.load();
+        bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if(ok)
         {
-            ok = cudaMemcpyAsync(m->d_params, m->h_params, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
-            ok = ok && enqueue_batch(m, 1, m->d_params, m->d_lnew, m->stream) == LCU_OK;
-            ok = ok && cudaMemcpyAsync(m->h_lnew, m->d_lnew, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+            // The pinned staging buffers are mapped into the device's address space
+            // (unified addressing): set_params reads the point's few parameters straight
+            // from host memory and the reduction writes the result there, which takes
+            // the two copy nodes (and their dependencies) out of the graph.  LCU_GRAPH_COPIES
+            // restores them.
+            float* dp = nullptr;
+            double* dl = nullptr;
+            mapped = !getenv("LCU_GRAPH_COPIES")
+                && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dp), m->h_params, 0) == cudaSuccess
+                && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dl), m->h_lnew, 0) == cudaSuccess && dp && dl;
+            if(!mapped)
+                cudaGetLastError();
+            const size_t po = (size_t)slot*m->npars;
+            if(mapped)
+                ok = enqueue_batch(m, 1, dp + po, dl + slot, m->stream) == LCU_OK;
+            else
+            {
+                ok = cudaMemcpyAsync(m->d_params + po, m->h_params + po, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream) == cudaSuccess;
+                ok = ok && enqueue_batch(m, 1, m->d_params + po, m->d_lnew + slot, m->stream) == LCU_OK;
+                ok = ok && cudaMemcpyAsync(m->h_lnew + slot, m->d_lnew + slot, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
+            }
+            ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
         }
-        ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
-    }
-    // captured launches have not run: they count each time the graph is launched
-    m->graph1_nodes = (unsigned)(g_launches.load() - launches0);
-    g_launches.fetch_sub(m->graph1_nodes, std::memory_order_relaxed);
-    if(ok)
-        ok = cudaGraphInstantiate(&m->graph1, graph, 0) == cudaSuccess;
-    if(graph)
-        cudaGraphDestroy(graph);
-    if(!ok)
-    {
-        cudaGetLastError();
-        m->graph1 = nullptr;
-        m->graph1_off = true;
-        return false;
+        // captured launches have not run: they count each time the graph is launched
+        m->graph1_nodes = (unsigned)(g_launches.load() - launches0);
+        g_launches.fetch_sub(m->graph1_nodes, std::memory_order_relaxed);
+        if(ok)
+            ok = cudaGraphInstantiate(slot == 0 ? &m->graph1 : &m->graph1b, graph, 0) == cudaSuccess;
+        if(graph)
+            cudaGraphDestroy(graph);
+        if(!ok)
+        {
+            cudaGetLastError();
+            drop_point_graphs(m);
+            m->graph1_off = true;
+            return false;
+        }
     }
     m->graph1_rows[0] = m->row0;
     m->graph1_rows[1] = m->row1;
@@ -593,8 +595,9 @@ void destroy_device_state(lcu_model* m)
 {
     if(m->ctx && m->ctx->device >= 0)
         cudaSetDevice(m->ctx->device);
-    if(m->graph1)
-        cudaGraphExecDestroy(m->graph1);
+    drop_point_graphs(m);
+    for(cudaEvent_t& e : m->async_done)
+        if(e) { cudaEventDestroy(e); e = nullptr; }
     for(cudaEvent_t& e : m->ev_io)
         if(e) { cudaEventDestroy(e); e = nullptr; }
     for(lcu_model::EventSet& es : m->evsets)
@@ -1281,6 +1284,11 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
         set_error("lcu_loglike_batch: null argument");
         return LCU_E_ARG;
     }
+    if(m->async_busy[0] || m->async_busy[1])
+    {
+        set_error("lcu_loglike_batch: evaluations started with lcu_loglike_async are still in flight (lcu_loglike_wait them first)");
+        return LCU_E_ARG;
+    }
     RT_CHECK(cudaSetDevice(m->ctx->device));
     rc = ensure_stage(m, nbatch);
     if(rc) return rc;
@@ -1337,6 +1345,75 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
         if(cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) m->prof.download_ms += t;
         harvest_profile(m);
     }
+    return LCU_OK;
+}
+
+// the NaN pattern that marks a result word as pending (no arithmetic produces it)
+static const unsigned long long LCU_PENDING = 0x7ff8dead5eed0001ull;
+
+int lcu_loglike_async(lcu_model* m, const float* params, int* ticket)
+{
+    int rc = need_device(m, "lcu_loglike_async");
+    if(rc) return rc;
+    if(!params || !ticket)
+    {
+        set_error("lcu_loglike_async: null argument");
+        return LCU_E_ARG;
+    }
+    const int slot = m->async_next;
+    if(m->async_busy[slot])
+    {
+        set_error("lcu_loglike_async: two evaluations are in flight already (lcu_loglike_wait one of them first)");
+        return LCU_E_ARG;
+    }
+    RT_CHECK(cudaSetDevice(m->ctx->device));
+    rc = ensure_stage(m, 2);
+    if(rc) return rc;
+    if(!m->async_done[slot])
+        RT_CHECK(cudaEventCreateWithFlags(&m->async_done[slot], cudaEventDisableTiming));
+    const size_t po = (size_t)slot*m->npars;
+    memcpy(m->h_params + po, params, m->npars*sizeof(float));
+    volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(m->h_lnew + slot);
+    *word = LCU_PENDING;
+    if(!m->profile && single_point_graph(m))
+    {
+        RT_CHECK(cudaGraphLaunch(slot == 0 ? m->graph1 : m->graph1b, m->stream));
+        g_launches.fetch_add(m->graph1_nodes, std::memory_order_relaxed);
+    }
+    else
+    {
+        RT_CHECK(cudaMemcpyAsync(m->d_params + po, m->h_params + po, m->npars*sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        rc = enqueue_batch(m, 1, m->d_params + po, m->d_lnew + slot, m->stream);
+        if(rc) return rc;
+        RT_CHECK(cudaMemcpyAsync(m->h_lnew + slot, m->d_lnew + slot, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    RT_CHECK(cudaEventRecord(m->async_done[slot], m->stream));
+    m->async_busy[slot] = true;
+    m->async_next = 1 - slot;
+    *ticket = slot;
+    return LCU_OK;
+}
+
+int lcu_loglike_wait(lcu_model* m, int ticket, double* lnew)
+{
+    int rc = need_device(m, "lcu_loglike_wait");
+    if(rc) return rc;
+    if(ticket < 0 || ticket > 1 || !lnew || !m->async_busy[ticket])
+    {
+        set_error("lcu_loglike_wait: no evaluation in flight under ticket %d", ticket);
+        return LCU_E_ARG;
+    }
+    volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(m->h_lnew + ticket);
+    if(!getenv("LCU_NO_POLL"))
+        for(unsigned spins = 1; *word == LCU_PENDING; ++spins)
+            if((spins & 0xfff) == 0 && cudaEventQuery(m->async_done[ticket]) != cudaErrorNotReady)
+                break;
+    m->async_busy[ticket] = false;
+    if(*word == LCU_PENDING)
+        RT_CHECK(cudaEventSynchronize(m->async_done[ticket]));
+    *lnew = m->h_lnew[ticket];
+    if(m->profile)
+        harvest_profile(m);
     return LCU_OK;
 }
 

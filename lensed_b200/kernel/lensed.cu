@@ -204,8 +204,14 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
         __shared__ __align__(16) uint sdata[LCU_WORDS];
         if constexpr(FOLD)
         {
+            // one coalesced read of the point's parameters per block (they may live in
+            // mapped host memory: one bus transaction, not LCU_NPARS of them)
+            __shared__ float sparams[LCU_NPARS > 0 ? LCU_NPARS : 1];
+            if(threadIdx.x < LCU_NPARS)
+                sparams[threadIdx.x] = a.params[(size_t)b*LCU_NPARS + threadIdx.x];
+            __syncthreads();
             if(threadIdx.x == 0)
-                lcu_set_params_block(sdata, a.params + (size_t)b*LCU_NPARS);
+                lcu_set_params_block(sdata, sparams);
         }
         else
         {

@@ -177,6 +177,28 @@ static int latency(int device, size_t size, int n)
     clock_gettime(CLOCK_MONOTONIC, &t1);
     const double us = ((double)(t1.tv_sec - t0.tv_sec)*1e9 + (double)(t1.tv_nsec - t0.tv_nsec))/1e3/n;
     printf("latency %.3f us per lcu_loglike (%d calls, %zux%zu, sie + sersic, 9x9 PSF, g3k7) checksum %.9g\n", us, n, size, size, sum);
+    /* the same points with two evaluations in flight (lcu_loglike_async / _wait): what a host
+       that prepares point i + 1 while point i is evaluated sees per point */
+    double sum2 = 0;
+    int ticket = -1, next;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for(int i = 0; i < n; ++i)
+    {
+        p[3] = 0.75f + 1e-4f*(float)(i & 15);
+        CHECK(lcu_loglike_async(model, p, &next));
+        if(ticket >= 0)
+        {
+            CHECK(lcu_loglike_wait(model, ticket, &lnew));
+            sum2 += lnew;
+        }
+        ticket = next;
+    }
+    CHECK(lcu_loglike_wait(model, ticket, &lnew));
+    sum2 += lnew;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double us2 = ((double)(t1.tv_sec - t0.tv_sec)*1e9 + (double)(t1.tv_nsec - t0.tv_nsec))/1e3/n;
+    printf("pipelined %.3f us per point with two in flight (lcu_loglike_async / lcu_loglike_wait) checksum %.9g %s\n",
+           us2, sum2, sum2 == sum ? "same" : "DIFFERENT");
     lcu_model_destroy(model);
     lcu_destroy(ctx);
     free(qq); free(ww); free(image); free(weight);

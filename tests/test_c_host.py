@@ -80,3 +80,7 @@ def test_single_point_latency_from_c(host_check):
     print(out)
     us = float(out.split()[1])
     assert 0 < us < 200
+    # two in flight: same checksum (same bits in the same order), and no slower per point
+    second = out.splitlines()[1].split()
+    assert second[0] == "pipelined" and second[-1] == "same"
+    assert 0 < float(second[1]) < 200

@@ -15,13 +15,13 @@ ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
     cfg = H.example_config(name)
     res = {}
-    for mode in ("graph", "graph_separate_set_params", "plain"):
-        for env in ("LCU_NO_GRAPH", "LCU_NO_FOLD_SETTER"):
+    for mode in ("graph", "graph_folded_set_params", "plain"):
+        for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER"):
             os.environ.pop(env, None)
         if mode == "plain":
             os.environ["LCU_NO_GRAPH"] = "1"
-        elif mode == "graph_separate_set_params":
-            os.environ["LCU_NO_FOLD_SETTER"] = "1"
+        elif mode == "graph_folded_set_params":
+            os.environ["LCU_FOLD_SETTER"] = "1"
         m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
         for _ in range(20):
             v = m.loglike(cfg.params)
@@ -31,9 +31,21 @@ for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
             v = m.loglike(cfg.params)
         dt = (time.perf_counter() - t0)/n
         res[mode] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, lnew=v)
+        if mode == "graph":
+            # two evaluations in flight (lcu_loglike_async / lcu_loglike_wait)
+            t0 = time.perf_counter()
+            t = m.loglike_async(cfg.params)
+            for _ in range(n - 1):
+                tn = m.loglike_async(cfg.params)
+                v2 = m.loglike_wait(t)
+                t = tn
+            v2 = m.loglike_wait(t)
+            dt = (time.perf_counter() - t0)/n
+            assert v2 == v
+            res["graph_two_in_flight"] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, lnew=v2)
         m.close()
-    assert res["graph"]["lnew"] == res["plain"]["lnew"] == res["graph_separate_set_params"]["lnew"]
-    for env in ("LCU_NO_GRAPH", "LCU_NO_FOLD_SETTER"):
+    assert res["graph"]["lnew"] == res["plain"]["lnew"] == res["graph_folded_set_params"]["lnew"]
+    for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER"):
         os.environ.pop(env, None)
     try:
         from oracle import pyoracle as O
