@@ -569,7 +569,8 @@ def parity_record(model, w, image, weight, P, lnew_gpu):
     o64 = O.Model(w["objects"], image, weight, qq, ww, psf=w["psf"], variant="f64")
     out = model.render(w["truth"], error=False, chi=False)
     rec = {"point": "truth", "criterion": "flat: |gpu - o32|/|o32| <= 1e-5 per pixel, <= 1e-6 for lnew (north_star); "
-           "floor: |gpu - f64| <= 1.5 |o32 - f64| (no further from the exact answer than the reference's own float32 arithmetic)"}
+           "floor: |gpu - f64| <= 2 |o32 - f64| (no further from the exact answer than the reference's own float32 arithmetic; "
+           "tests/test_gpu_parity.py has the criterion and its ensemble of float32 realisations)"}
     raw32, _ = o32.render(w["truth"])
     raw64, _ = o64.render(w["truth"])
     l32, m32, _ = o32.loglike(w["truth"], want_maps=True)
@@ -583,7 +584,7 @@ def parity_record(model, w, image, weight, P, lnew_gpu):
         rec[key] = {"max": float(e.max()), "p99.9": float(np.quantile(e, 0.999)), "median": float(np.median(e)),
                     "floor_max": float(fl.max()), "floor_p99.9": float(np.quantile(fl, 0.999)),
                     "gpu_vs_f64_max": float(e64.max()), "gpu_vs_f64_p99.9": float(np.quantile(e64, 0.999)),
-                    "flat_ok": bool(e.max() <= 1e-5), "floor_ok": bool(e64.max() <= 1.5*fl.max())}
+                    "flat_ok": bool(e.max() <= 1e-5), "floor_ok": bool(e64.max() <= 2.0*fl.max())}
     pts = [("truth", w["truth"], model.loglike(w["truth"]), l32, l64)]
     for i in range(min(2, len(P))):
         pts.append((f"batch[{i}] (1 % off the truth)", P[i], float(lnew_gpu[i]), o32.loglike(P[i]), o64.loglike(P[i])))

@@ -46,7 +46,8 @@ def _get(mem, addr, shape, dtype=np.float32):
 
 def _render_args(cfg, pcs, nk, value, partial, ngroups, mode, error=0, objs=0, tail=(0, 0, 0.0), k0=0):
     # lcu_render_args of kernel/lensed.cu: pcs, k0, nk, objs, value, error, image, weight, chimap, partial, ngroups, mode, tail
-    a = struct.pack("<4fqqQQQQQQQiiQQd", *pcs, k0, nk, objs, value, error, IMG, WGT, 0, partial, ngroups, mode, *tail)
+    # lcu_render_args (kernel/lensed.cu): pcs, k0, nk, objs, params (fold kernels only), value, error, image, weight, chimap, partial, ...
+    a = struct.pack("<4fqqQQQQQQQQiiQQd", *pcs, k0, nk, objs, 0, value, error, IMG, WGT, 0, partial, ngroups, mode, *tail)
     return a + b"\0"*(128 - len(a))
 
 
