@@ -170,6 +170,7 @@ struct lcu_model
     CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_conv_small = nullptr, f_reduce = nullptr;
     CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
     CUfunction f_render_fold[4] = {};                                   // split kernels with set_params folded in
+    CUfunction f_render_q[4] = {};                                      // split kernels, two quadrature points per pass (if pair)
     CUfunction f_make_weight = nullptr;
     bool pair = false;
     CUdeviceptr c_objs = 0;
@@ -402,8 +403,12 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
             rc = launch(m, a.error ? m->f_render_pair_err : m->f_render_pair, dim3((unsigned)div_up(nk, 512), (unsigned)nb),
                         dim3(256), args, st);
         else
-            rc = launch(m, a.error ? m->f_render_err[idx] : fold ? m->f_render_fold[idx] : m->f_render[idx],
+        {
+            // split kernels: pairable models shoot two quadrature points per pass (LCU_NO_SPLIT_PAIR: one)
+            const bool q2 = split > 1 && m->pair && !a.error && !fold && !getenv("LCU_NO_SPLIT_PAIR");
+            rc = launch(m, a.error ? m->f_render_err[idx] : fold ? m->f_render_fold[idx] : q2 ? m->f_render_q[idx] : m->f_render[idx],
                         dim3((unsigned)div_up(nk, 256/split), (unsigned)nb), dim3(256), args, st);
+        }
         if(rc) return rc;
     }
     if(ev) cudaEventRecord(ev[2], st);
@@ -1070,6 +1075,9 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     if(m->pair)
     {
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair, m->mod, "lcu_render_pair")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_q[1], m->mod, "lcu_render_q_s2")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_q[2], m->mod, "lcu_render_q_s4")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_q[3], m->mod, "lcu_render_q_s8")));
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair_err, m->mod, "lcu_render_pair_err")));
     }
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));

@@ -175,7 +175,13 @@ __device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsig
 // ERR: also accumulate the quadrature error estimate (second weight); only
 // the dumper asks for it, the likelihood path does not pay for it
 // FOLD: the block computes its point's object block itself (lcu_set_params_block)
-template<int S, bool ERR, bool FOLD = false>
+// PAIRQ (split kernels of pairable models): a thread shoots two quadrature points
+// of its pixel per pass through lcu_compute2() -- the packed two-rays code of
+// shim.cuh with the lanes on consecutive points instead of on two pixels -- which
+// halves the chain of dependent ray evaluations of a small launch (7 -> 4 for rule
+// g3k7 shared by 8 warps).  Each lane computes the one-ray bits, the values land
+// in the same shared-memory slots and are added up in the same order.
+template<int S, bool ERR, bool FOLD = false, bool PAIRQ = false>
 __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 {
     constexpr int P = LCU_BLOCK/S;          // pixels per block
@@ -280,11 +286,29 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
         for(int c0 = 0; c0 < QUAD_POINTS; c0 += LCU_CHUNK)
         {
             const int c1 = min(c0 + LCU_CHUNK, QUAD_POINTS);
-#pragma unroll 1
-            for(int n = c0 + ns; n < c1; n += S)
+#if LCU_PAIR
+            if constexpr(PAIRQ)
             {
-                const float4 q = lcu_quad[n];
-                sc[pl][n - c0] = lcu_compute(data, float2(__fadd_rn(x.x, q.x), __fadd_rn(x.y, q.y)));
+#pragma unroll 1
+                for(int n = c0 + 2*ns; n < c1; n += 2*S)
+                {
+                    const int n1 = min(n + 1, c1 - 1);      // odd tail: the second lane repeats the last point, result dropped
+                    const float4 q0 = lcu_quad[n], q1 = lcu_quad[n1];
+                    const lcu_pf c = lcu_compute2(data, lcu_pf2(lcu_pf(x.x) + lcu_pf(q0.x, q1.x), lcu_pf(x.y) + lcu_pf(q0.y, q1.y)));
+                    sc[pl][n - c0] = c.lo();
+                    if(n + 1 < c1)
+                        sc[pl][n + 1 - c0] = c.hi();
+                }
+            }
+            else
+#endif
+            {
+#pragma unroll 1
+                for(int n = c0 + ns; n < c1; n += S)
+                {
+                    const float4 q = lcu_quad[n];
+                    sc[pl][n - c0] = lcu_compute(data, float2(__fadd_rn(x.x, q.x), __fadd_rn(x.y, q.y)));
+                }
             }
             __syncthreads();
             if(ns == 0)
@@ -363,6 +387,16 @@ LCU_RENDER_KERNEL(8)
 LCU_RENDER_FOLD_KERNEL(2)
 LCU_RENDER_FOLD_KERNEL(4)
 LCU_RENDER_FOLD_KERNEL(8)
+
+#if LCU_PAIR
+// the split kernels with two quadrature points per thread and pass (small launches of pairable models)
+#define LCU_RENDER_Q_KERNEL(S) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
+    lcu_render_q_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, false, false, true>(a); }
+LCU_RENDER_Q_KERNEL(2)
+LCU_RENDER_Q_KERNEL(4)
+LCU_RENDER_Q_KERNEL(8)
+#endif
 
 #if LCU_PAIR
 // Two rays per thread (shim.cuh: packed pairs).  A warp covers 64 consecutive

@@ -308,6 +308,25 @@ def test_batch_and_split_invariance(gpu_ctx, monkeypatch):
         assert np.array_equal(m.loglike_batch(P), base), f"split {split}"
         img = m.render(P[0])
         assert np.array_equal(img["raw"], img0["raw"]) and np.array_equal(img["error"], img0["error"])
+        # the split kernels shoot two quadrature points per pass for pairable models (lcu_render_q_s*): one per pass instead
+        monkeypatch.setenv("LCU_NO_SPLIT_PAIR", "1")
+        assert np.array_equal(m.loglike_batch(P), base), f"split {split}, one point per pass"
+        monkeypatch.delenv("LCU_NO_SPLIT_PAIR")
+    monkeypatch.delenv("LCU_SPLIT")
+    # the same on the reference's examples (rule g3k7: 49 points = chunks of 32 + 17, an odd tail) and a one-point rule
+    for cfg2 in (H.example_config("test_sersic_bulge"), H.example_config("full_mock_nopsf"),
+                 H.Config("point-rule", cfg.objects, cfg.params, cfg.image, cfg.weight, rule="point", psf=cfg.psf),
+                 H.Config("gm75-rule", cfg.objects, cfg.params, cfg.image, cfg.weight, rule="gm75")):
+        m3 = cfg2.product(gpu_ctx)
+        P3 = np.stack([cfg2.params, cfg2.params*np.float32(1.001)])
+        a = m3.loglike_batch(P3)
+        one = np.array([m3.loglike(p) for p in P3])
+        monkeypatch.setenv("LCU_NO_SPLIT_PAIR", "1")
+        m4 = cfg2.product(gpu_ctx)
+        assert np.array_equal(m4.loglike_batch(P3), a) and np.array_equal(np.array([m4.loglike(p) for p in P3]), one), cfg2.name
+        monkeypatch.delenv("LCU_NO_SPLIT_PAIR")
+        assert np.array_equal(a, one), cfg2.name
+        m3.close(); m4.close()
 
 
 def test_row_strips_add_up(gpu_ctx):

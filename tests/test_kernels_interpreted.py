@@ -31,6 +31,7 @@ import test_pair_rays as R  # noqa: E402
 pytest.importorskip("cuda.bindings.nvrtc")
 
 IMG, WGT, RAW, MODEL, PART, LNEW, RAW1, PART1, MODEL1, ERR, OBJS, COUNTER, LNEW8, RAW8, PART8 = (0x100000*k for k in range(1, 16))
+RAWQ, PARTQ, LNEWQ = 0x100000*30, 0x100000*31, 0x100000*32
 OUT_VALUE, OUT_ERROR, OUT_CHI2 = 1, 2, 4
 
 
@@ -136,6 +137,20 @@ def test_render_and_reduce_without_psf():
              [_render_args(cfg, cfg.pcs, npix, RAW8, PART8, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS)], mem, consts)
     assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAW8, (npix,)).view(np.uint32))
     assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PART8, (2*ngroups,)).view(np.uint32))
+    # the split kernels of pairable models: two quadrature points per thread and pass through lcu_compute2 -- the same
+    # image, partial sums and fused log-likelihood, bit for bit (eight warps with the fused tail, then two warps)
+    mem[COUNTER] = 0
+    M.launch("lcu_render_q_s8", ((npix + 31)//32, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAWQ, PARTQ, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS, tail=(LNEWQ, COUNTER, -0.5))],
+             mem, consts)
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAWQ, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PARTQ, (2*ngroups,)).view(np.uint32))
+    assert np.array_equal(_get(mem, LNEW, (2,)).view(np.uint32), _get(mem, LNEWQ, (2,)).view(np.uint32))
+    assert mem[COUNTER] == 0
+    M.launch("lcu_render_q_s2", ((npix + 127)//128, 1), 256,
+             [_render_args(cfg, cfg.pcs, npix, RAWQ, PARTQ, ngroups, OUT_VALUE | OUT_CHI2, objs=OBJS)], mem, consts)
+    assert np.array_equal(_get(mem, RAW, (npix,)).view(np.uint32), _get(mem, RAWQ, (npix,)).view(np.uint32))
+    assert np.array_equal(_get(mem, PART, (2*ngroups,)).view(np.uint32), _get(mem, PARTQ, (2*ngroups,)).view(np.uint32))
     # the quadrature error image (the dumper's ERR layer) from the pair kernel
     M.launch("lcu_render_pair_err", ((npix + 511)//512, 1), 256,
              [_render_args(cfg, cfg.pcs, npix, RAW1, 0, ngroups, OUT_VALUE | OUT_ERROR, error=ERR)], mem, consts)

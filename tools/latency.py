@@ -15,13 +15,15 @@ ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
     cfg = H.example_config(name)
     res = {}
-    for mode in ("graph", "graph_folded_set_params", "plain"):
-        for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER"):
+    for mode in ("graph", "graph_one_point_per_pass", "graph_folded_set_params", "plain"):
+        for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR"):
             os.environ.pop(env, None)
         if mode == "plain":
             os.environ["LCU_NO_GRAPH"] = "1"
         elif mode == "graph_folded_set_params":
             os.environ["LCU_FOLD_SETTER"] = "1"
+        elif mode == "graph_one_point_per_pass":
+            os.environ["LCU_NO_SPLIT_PAIR"] = "1"
         m = cfg.product(ctx, flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
         for _ in range(20):
             v = m.loglike(cfg.params)
@@ -45,7 +47,8 @@ for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
             res["graph_two_in_flight"] = dict(us_per_eval=dt*1e6, evals_per_s=1/dt, lnew=v2)
         m.close()
     assert res["graph"]["lnew"] == res["plain"]["lnew"] == res["graph_folded_set_params"]["lnew"]
-    for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER"):
+    assert res["graph"]["lnew"] == res["graph_one_point_per_pass"]["lnew"]
+    for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR"):
         os.environ.pop(env, None)
     try:
         from oracle import pyoracle as O
