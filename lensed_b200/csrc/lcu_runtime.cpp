@@ -169,7 +169,8 @@ struct lcu_model
     CUmodule mod = nullptr;
     CUfunction f_set = nullptr, f_render[4] = {}, f_render_err[4] = {}, f_conv = nullptr, f_conv_small = nullptr, f_reduce = nullptr;
     CUfunction f_render_pair = nullptr, f_render_pair_err = nullptr;   // two rays per thread, if pair
-    CUfunction f_render_fold[4] = {};                                   // split kernels with set_params folded in
+    CUfunction f_render_fold[4] = {};                                   // split kernels with set_params folded in (if fold)
+    bool fold = false;                                                  // LCU_FOLD_SETTER=1 when the model was created
     CUfunction f_render_q[4] = {};                                      // split kernels, two quadrature points per pass (if pair)
     CUfunction f_make_weight = nullptr;
     bool pair = false;
@@ -348,8 +349,7 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
     // takes one kernel and one dependency out of the launch sequence
     // (lcu_set_params_block: the same code, the same bits).  Measured slower than the
     // separate kernel, hence not the default.
-    const char* fold_env = getenv("LCU_FOLD_SETTER");
-    const bool fold = split > 1 && nb <= 4 && !error && fold_env && *fold_env == '1';
+    const bool fold = m->fold && split > 1 && nb <= 4 && !error;
     // set_params, src/nested.c:77
     if(!fold)
     {
@@ -864,6 +864,10 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     m->flags = desc->flags;
     m->obj_const = !(desc->flags & LCU_OBJ_SHARED);
     // two rays per thread if every object's per-ray code can be typed as pairs
+    {
+        const char* fold_env = getenv("LCU_FOLD_SETTER");
+        m->fold = fold_env && *fold_env == '1';
+    }
     m->pair = !(desc->flags & LCU_NO_PAIR);
     for(const ModelObject& o : m->objs)
         m->pair = m->pair && o.info->pairable;
@@ -960,7 +964,8 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "#define LCU_NPARS " << std::max<size_t>(m->npars, 1) << "\n"
           << "#define LCU_MAXB " << m->maxb << "\n"
           << "#define LCU_OBJ_CONST " << (m->obj_const ? 1 : 0) << "\n"
-          << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n";
+          << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n"
+          << "#define LCU_FOLD " << (m->fold ? 1 : 0) << "\n";
         if(pair_minblocks)
             s << "#define LCU_PAIR_MINBLOCKS " << pair_minblocks << "\n";
         s << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
@@ -1065,9 +1070,12 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[1], m->mod, "lcu_render_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[2], m->mod, "lcu_render_s4")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render[3], m->mod, "lcu_render_s8")));
-    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[1], m->mod, "lcu_render_fold_s2")));
-    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[2], m->mod, "lcu_render_fold_s4")));
-    M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[3], m->mod, "lcu_render_fold_s8")));
+    if(m->fold)
+    {
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[1], m->mod, "lcu_render_fold_s2")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[2], m->mod, "lcu_render_fold_s4")));
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_fold[3], m->mod, "lcu_render_fold_s8")));
+    }
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[0], m->mod, "lcu_render_err_s1")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[1], m->mod, "lcu_render_err_s2")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_err[2], m->mod, "lcu_render_err_s4")));
@@ -1175,12 +1183,20 @@ int lcu_model_set_rows(lcu_model* m, size_t row0, size_t row1)
         set_error("lcu_model_set_rows: invalid row range");
         return LCU_E_ARG;
     }
+    if(m->async_busy[0] || m->async_busy[1])
+    {
+        set_error("lcu_model_set_rows: evaluations started with lcu_loglike_async are still in flight (lcu_loglike_wait them first)");
+        return LCU_E_ARG;
+    }
     m->row0 = row0;
     m->row1 = row1;
     return LCU_OK;
 }
 
-static int need_device(const lcu_model* m, const char* fn)
+// `idle`: the call uses or changes state that evaluations started with lcu_loglike_async
+// are still reading (staging slots, scratch buffers, data, row range): refuse it until they
+// have been waited for
+static int need_device(const lcu_model* m, const char* fn, bool idle = true)
 {
     if(!m)
     {
@@ -1191,6 +1207,11 @@ static int need_device(const lcu_model* m, const char* fn)
     {
         set_error("%s: compile-only context has no device (there is no CPU fallback)", fn);
         return LCU_E_NODEVICE;
+    }
+    if(idle && (m->async_busy[0] || m->async_busy[1]))
+    {
+        set_error("%s: evaluations started with lcu_loglike_async are still in flight (lcu_loglike_wait them first)", fn);
+        return LCU_E_ARG;
     }
     return LCU_OK;
 }
@@ -1292,11 +1313,6 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
         set_error("lcu_loglike_batch: null argument");
         return LCU_E_ARG;
     }
-    if(m->async_busy[0] || m->async_busy[1])
-    {
-        set_error("lcu_loglike_batch: evaluations started with lcu_loglike_async are still in flight (lcu_loglike_wait them first)");
-        return LCU_E_ARG;
-    }
     RT_CHECK(cudaSetDevice(m->ctx->device));
     rc = ensure_stage(m, nbatch);
     if(rc) return rc;
@@ -1361,7 +1377,7 @@ static const unsigned long long LCU_PENDING = 0x7ff8dead5eed0001ull;
 
 int lcu_loglike_async(lcu_model* m, const float* params, int* ticket)
 {
-    int rc = need_device(m, "lcu_loglike_async");
+    int rc = need_device(m, "lcu_loglike_async", false);
     if(rc) return rc;
     if(!params || !ticket)
     {
@@ -1404,7 +1420,7 @@ int lcu_loglike_async(lcu_model* m, const float* params, int* ticket)
 
 int lcu_loglike_wait(lcu_model* m, int ticket, double* lnew)
 {
-    int rc = need_device(m, "lcu_loglike_wait");
+    int rc = need_device(m, "lcu_loglike_wait", false);
     if(rc) return rc;
     if(ticket < 0 || ticket > 1 || !lnew || !m->async_busy[ticket])
     {

@@ -380,13 +380,17 @@ LCU_RENDER_KERNEL(2)
 LCU_RENDER_KERNEL(4)
 LCU_RENDER_KERNEL(8)
 
-// the split kernels with set_params folded in (small launches, likelihood path only)
+// the split kernels with set_params folded in (small launches, likelihood path only); an
+// experiment that measured slower than the separate kernel: compiled
+// only into models created with LCU_FOLD_SETTER=1 in the environment
+#if LCU_FOLD
 #define LCU_RENDER_FOLD_KERNEL(S) \
     extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
     lcu_render_fold_s##S(const __grid_constant__ lcu_render_args a) { lcu_render_impl<S, false, true>(a); }
 LCU_RENDER_FOLD_KERNEL(2)
 LCU_RENDER_FOLD_KERNEL(4)
 LCU_RENDER_FOLD_KERNEL(8)
+#endif
 
 #if LCU_PAIR
 // the split kernels with two quadrature points per thread and pass (small launches of pairable models)

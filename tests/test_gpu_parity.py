@@ -60,6 +60,8 @@ MATH_MODES = [pytest.param(0, id="strict"), pytest.param(FAST, id="fast")]
 # pinned separately by the flat 1e-5 bound on the 99.9th percentile.)
 FLOOR_K = 2.0
 FLOOR_K_MAX = 2.0
+import os as _os
+FULL_RECORD = bool(_os.environ.get("LCU_PARITY_FULL_RECORD"))
 _REPORT = []
 
 
@@ -100,7 +102,10 @@ def _check_lnew(cfg, params, got, flat=False, tag="", om=None):
     om = om or cfg.oracle()
     l32 = om.loglike(params)
     l64 = cfg.oracle(variant="f64").loglike(params)
-    others = {k: v.loglike(params) for k, v in _realisations(cfg).items()}
+    flat_ok = bool(abs(got - l32) <= LOGLIKE_TOL*abs(l32))
+    # the other float32 realisations are evaluated where the verdict needs them, or everywhere for the
+    # committed record (LCU_PARITY_FULL_RECORD=1: profiles/r02_parity_report.json)
+    others = {k: v.loglike(params) for k, v in _realisations(cfg).items()} if (FULL_RECORD or not flat_ok) else {}
     floor = max([abs(l32 - l64)] + [abs(v - l64) for v in others.values()])
     n = cfg.image.size
     rec = dict(case=cfg.name, what="lnew", tag=tag, gpu=got, o32=l32, f64=l64, rel_vs_o32=abs(got - l32)/abs(l32),
@@ -129,8 +134,9 @@ def _check_images(out, cfg, om, flat=False, tag=""):
     v64, _ = o64.render(cfg.params)
     _, m64, _ = o64.loglike(cfg.params, want_maps=True)
     others = {}
-    for k, o in _realisations(cfg).items():
-        others[k] = {"raw": o.render(cfg.params)[0], "model": o.loglike(cfg.params, want_maps=True)[1]}
+    if FULL_RECORD or any(H.rel_err(out[key], ref).max() > PIXEL_TOL for key, ref in (("raw", value), ("model", model))):
+        for k, o in _realisations(cfg).items():
+            others[k] = {"raw": o.render(cfg.params)[0], "model": o.loglike(cfg.params, want_maps=True)[1]}
     stats = {}
     for key, ref, ref64 in (("raw", value, v64), ("model", model, m64)):
         r = H.rel_err(out[key], ref)
@@ -624,6 +630,10 @@ def test_async_pair_same_bits_two_in_flight(gpu_ctx, monkeypatch, env):
             m.loglike_async(P[2])
         with pytest.raises(L.LensedCudaError):
             m.loglike(P[2])
+        for call in (lambda: m.set_rows(0, 10), lambda: m.render(P[2]), lambda: m.set_params(P[2]),
+                     lambda: m.set_data(image=cfg.image), lambda: m.loglike_batch(P)):
+            with pytest.raises(L.LensedCudaError, match="in flight"):
+                call()                                        # nothing may touch the model's state while tickets are out
         assert m.loglike_wait(t0) == ref[0]
         with pytest.raises(L.LensedCudaError):
             m.loglike_wait(t0)                                # redeemed already
