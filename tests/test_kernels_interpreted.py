@@ -198,7 +198,7 @@ def test_render_convolve_reduce_with_psf():
 def test_power_law_lens_with_written_out_pair_math():
     """epl_plus_shear + sersic through lcu_render_pair built with
     -DLCU_PF_LIBM_PAIR=1 (atan2 / sincos / powr of pairs as packed arithmetic,
-    off by default): the one-ray kernel's bits, the oracle's image."""
+    the default since round 2): the one-ray kernel's bits, the oracle's image."""
     from lensed_b200 import api
     base = H.golden_config("epl_plus_shear")
     h, w = 8, 12

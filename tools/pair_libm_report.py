@@ -100,7 +100,7 @@ def main():
     from lensed_b200 import workloads as W
     w = W.c5(4096)
     img = np.zeros((w["height"], w["width"]), np.float32)
-    for tag, env in (("off", ""), ("on ", "-DLCU_PF_LIBM_PAIR=1")):
+    for tag, env in (("off", "-DLCU_PF_LIBM_PAIR=0"), ("on ", "-DLCU_PF_LIBM_PAIR=1")):
         os.environ["LCU_NVRTC_FLAGS"] = env
         m = L.Model(L.Context(device=-1, objects_dir=os.path.join(ROOT, "tests", "golden", "objects")), w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=flags)
         print(tag, m.kernel_usage("lcu_render_pair"))
@@ -115,8 +115,8 @@ ray level       tests/test_pair_rays.py            lcu_compute2 = lcu_compute on
 kernel level    tests/test_kernels_interpreted.py  lcu_render_pair = lcu_render_s1 (image and chi^2 partial sums) on an EPL scene and on
                                                    random models with power-law lenses; 42 more random models by hand
 ptxas           tests/test_pair_rays.py            packed instruction counts of lcu_render_pair equal in PTX and SASS (no contraction)
-hardware        tests/test_gpu_parity.py           test_two_rays_per_thread_same_bits_with_packed_libm: non-gating (xfail, not strict),
-                                                   runs with the GPU suite; XPASS = confirmed""")
+hardware        tests/test_gpu_parity.py           test_two_rays_per_thread_same_bits_packed_libm_switch: the switch in either
+                                                   position against the one-ray kernel, bit for bit (on by default since round 2)""")
 
 
 if __name__ == "__main__":
