@@ -52,15 +52,51 @@ class ShardedLikelihood:
 
     @classmethod
     def for_model(cls, model, mode: str = "points", group=None, device: Optional[str] = None):
-        """Bind to a lensed_b200.Model on this rank's GPU."""
-        return cls(model.loglike_batch, mode=mode, group=group, device=device, set_rows=model.set_rows,
+        """Bind to a lensed_b200.Model on this rank's GPU.  With a CUDA `device`
+        the batch stays on the device between the evaluation and the
+        all-reduce: parameters go up once from pinned memory, the C ABI's
+        device-pointer entry writes this rank's slots of the lnew vector, NCCL
+        reduces that vector in place and it comes down once."""
+        self = cls(model.loglike_batch, mode=mode, group=group, device=device, set_rows=model.set_rows,
                    height=model.height)
+        self.model = model if (device and str(device).startswith("cuda")) else None
+        self._bufs = None
+        return self
+
+    def _device_batch(self, params: np.ndarray) -> np.ndarray:
+        import torch
+        nbatch, npars = params.shape
+        if self._bufs is None or self._bufs[0].shape[0] < nbatch:
+            cap = max(nbatch, 64)
+            self._bufs = (torch.empty((cap, npars), dtype=torch.float32).pin_memory(),
+                          torch.empty((cap, npars), dtype=torch.float32, device=self.device),
+                          torch.empty(cap, dtype=torch.float64, device=self.device),
+                          torch.empty(cap, dtype=torch.float64).pin_memory())
+        h_par, d_par, d_lnew, h_lnew = self._bufs
+        stream = torch.cuda.current_stream(self.device)
+        h_par[:nbatch].copy_(torch.from_numpy(params))
+        d_par[:nbatch].copy_(h_par[:nbatch], non_blocking=True)
+        lnew = d_lnew[:nbatch]
+        if self.mode == "points":
+            b0, b1 = shard_range(nbatch, self.rank, self.world)
+            lnew.zero_()
+            if b1 > b0:
+                self.model.loglike_batch_device(b1 - b0, d_par[b0:b1].data_ptr(), lnew[b0:b1].data_ptr(), stream.cuda_stream)
+        else:
+            self.model.loglike_batch_device(nbatch, d_par.data_ptr(), lnew.data_ptr(), stream.cuda_stream)
+        if self.world > 1:
+            self.dist.all_reduce(lnew, op=self.dist.ReduceOp.SUM, group=self.group)
+        h_lnew[:nbatch].copy_(lnew, non_blocking=True)
+        stream.synchronize()
+        return h_lnew[:nbatch].numpy().copy()
 
     def loglike_batch(self, params) -> np.ndarray:
         """params[B, npars] (identical on every rank) -> lnew[B] on every rank."""
         import torch
         params = np.ascontiguousarray(params, dtype=np.float32)
         nbatch = params.shape[0]
+        if getattr(self, "model", None) is not None and nbatch > 0:
+            return self._device_batch(params)
         out = np.zeros(nbatch, np.float64)
         if self.mode == "points":
             b0, b1 = shard_range(nbatch, self.rank, self.world)
