@@ -436,6 +436,37 @@ def test_empty_and_ragged_batches(gpu_ctx):
         m.loglike_batch(np.zeros((3, m.npars + 1), np.float32))
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (1, 33), (3, 1), (2, 32), (5, 67)])
+@pytest.mark.parametrize("psf", [None, (3, 3), (4, 1)])
+def test_tiny_and_ragged_images(gpu_ctx, shape, psf):
+    """Images smaller than a warp, a tile or the PSF itself (every pixel an edge
+    pixel, most lanes dead): images, chi^2 map and log-likelihood against the
+    oracle; single point (graph path), a batch larger than the image, both
+    render kernels."""
+    import lensed_b200 as L
+    h, w = shape
+    rng = np.random.default_rng(h*100 + w)
+    wl = H.workloads.c4(max(8, max(shape)))
+    p = H.workloads.normalise_psf(rng.random((psf[1], psf[0])) + 0.1) if psf else None
+    img = rng.random(shape).astype(np.float32)
+    wht = (0.5 + rng.random(shape)).astype(np.float32)
+    cfg = H.Config(f"tiny-{h}x{w}", wl["objects"], wl["truth"], img, wht, rule="sub2", psf=p)
+    om = cfg.oracle()
+    P = H.workloads.param_batch(wl, 70)
+    ref = np.array([om.loglike(q) for q in P])
+    for flags in (0, L.LCU_NO_PAIR):
+        m = cfg.product(gpu_ctx, flags=flags)
+        out = m.render(cfg.params)
+        _, model, chi = om.loglike(cfg.params, want_maps=True)
+        assert H.rel_err(out["model"], model).max() <= PIXEL_TOL, cfg.name
+        assert np.allclose(out["chi"], chi, rtol=1e-4, atol=1e-6*max(chi.max(), 1e-30))
+        got = m.loglike_batch(P)
+        # a handful of pixels: no averaging over rounding noise, and chi^2 = w (m - d)^2 amplifies the 1e-5 of m by 2 m/|m - d|
+        assert np.all(np.abs(got - ref) <= 1e-4*np.abs(ref)), (cfg.name, np.abs(got - ref).max()/np.abs(ref).max())
+        assert m.loglike(P[3]) == got[3]
+        m.close()
+
+
 def test_full_size_c5_properties(gpu_ctx):
     """4096^2 / epl_plus_shear + 3 sersic + sky / g3k7 / 25x25 PSF."""
     w = H.workloads.c5(4096)
