@@ -44,6 +44,7 @@ struct Driver
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
 } drv;
 
 template<typename F>
@@ -67,7 +68,8 @@ bool init_driver()
     if(!resolve("cuModuleLoadData", &drv.ModuleLoadData) || !resolve("cuModuleUnload", &drv.ModuleUnload)
        || !resolve("cuModuleGetFunction", &drv.ModuleGetFunction)
        || !resolve("cuModuleGetGlobal", &drv.ModuleGetGlobal)
-       || !resolve("cuLaunchKernel", &drv.LaunchKernel) || !resolve("cuGetErrorString", &drv.GetErrorString))
+       || !resolve("cuLaunchKernel", &drv.LaunchKernel) || !resolve("cuGetErrorString", &drv.GetErrorString)
+       || !resolve("cuOccupancyMaxActiveBlocksPerMultiprocessor", &drv.OccupancyMaxActiveBlocks))
         return false;
     drv.ready = true;
     return true;
@@ -143,6 +145,24 @@ struct ConvolveArgs
     Tail tail;
 };
 
+// lcu_point_args of kernel/lensed.cu: with and without its PSF member
+struct PointArgsPsf
+{
+    RenderArgs r;
+    ConvolveArgs c;
+    uint32_t* objs;
+    unsigned* sync;
+    int conv_gx, conv_blocks;
+};
+
+struct PointArgsNoPsf
+{
+    RenderArgs r;
+    uint32_t* objs;
+    unsigned* sync;
+    int conv_gx, conv_blocks;
+};
+
 enum { OUT_VALUE = 1, OUT_ERROR = 2, OUT_CHI2 = 4, OUT_CHIMAP = 8 };
 
 } // namespace
@@ -172,6 +192,12 @@ struct lcu_model
     CUfunction f_render_fold[4] = {};                                   // split kernels with set_params folded in (if fold)
     bool fold = false;                                                  // LCU_FOLD_SETTER=1 when the model was created
     CUfunction f_render_q[4] = {};                                      // split kernels, two quadrature points per pass (if pair)
+    CUfunction f_point[4] = {};                                         // all stages of one point in one kernel (split 4 and 8)
+    size_t point_capacity[4] = {};                                      // blocks of f_point[] the device holds at once
+    bool point = false;                                                 // LCU_FUSED_POINT=1 when the model was created
+    bool point_off = false;                                             // a wait inside the kernel timed out once: not used again
+    bool point_ok = false;                                              // set while capturing a graph whose result word the host watches
+    unsigned* d_sync = nullptr;                                         // [2] hand-over words of f_point, zero between launches
     CUfunction f_make_weight = nullptr;
     bool pair = false;
     CUdeviceptr c_objs = 0;
@@ -193,6 +219,8 @@ struct lcu_model
     cudaGraphExec_t graph1b = nullptr;  // the same graph on the second staging slot (lcu_loglike_async)
     int async_next = 0;                 // slot the next lcu_loglike_async takes
     bool async_busy[2] = { false, false };
+    bool async_redone[2] = { false, false };    // the ticket's point was re-evaluated synchronously: answer in async_redo
+    double async_redo[2] = { 0, 0 };
     cudaEvent_t async_done[2] = { nullptr, nullptr };   // completion of a slot's evaluation when it is not watched
     bool graph1_off = false;
     size_t graph1_rows[2] = { 0, 0 };
@@ -350,6 +378,78 @@ int enqueue_points(lcu_model* m, size_t nb, const float* d_params, cudaStream_t 
     // (lcu_set_params_block: the same code, the same bits).  Measured slower than the
     // separate kernel, hence not the default.
     const bool fold = m->fold && split > 1 && nb <= 4 && !error;
+    // Opt-in (LCU_FUSED_POINT=1 when the model is created): one point of a small image
+    // with nothing but the log-likelihood asked for runs all stages in one kernel
+    // (lcu_point_s*, kernel/lensed.cu).  Correct and tested, but measured ~1 us SLOWER
+    // than the three launches, hence not the default.
+    if(nb == 1 && (split == 4 || split == 8) && want_chi2 && may_fuse && !value && !error && !model && !chimap && !fold && !ev
+       && m->point && m->point_ok && !m->point_off)
+    {
+        const int idx = split == 4 ? 2 : 3;
+        const size_t grid = div_up(nk, 256/(size_t)split);
+        const size_t rows = m->row1 - m->row0;
+        const size_t conv_gx = div_up(m->width, 32), conv_blocks = m->has_psf ? conv_gx*div_up(rows, 8) : 0;
+        const char* force = getenv("LCU_CONV_SMALL");
+        const bool conv_small_ok = !m->has_psf || !(force && *force == '0');
+        // at most conv_blocks blocks wait while they hold a slot: a quarter of the device's capacity at most
+        if(4*(conv_blocks + 1) <= m->point_capacity[idx] && conv_blocks <= grid && conv_small_ok)
+        {
+            const bool test_giveup = getenv("LCU_POINT_TEST_TIMEOUT") != nullptr;      // tests: block 0 never raises its flag
+            RenderArgs r;
+            memcpy(r.pcs, m->pcs, sizeof(r.pcs));
+            r.k0 = (long long)(r0*m->width);
+            r.nk = (long long)nk;
+            r.objs = nullptr;
+            r.params = d_params;
+            r.value = m->has_psf ? m->d_raw : nullptr;
+            r.error = nullptr;
+            r.image = m->d_image;
+            r.weight = m->d_weight;
+            r.chimap = nullptr;
+            r.partial = m->d_partial;
+            r.ngroups = ngroups;
+            r.mode = m->has_psf ? OUT_VALUE : OUT_CHI2;
+            r.tail = m->has_psf ? Tail{ nullptr, nullptr, 0 } : Tail{ reduce_out, m->d_counter, scale };
+            int rc;
+            if(m->has_psf)
+            {
+                PointArgsPsf a;
+                a.r = r;
+                a.c.raw = m->d_raw;
+                a.c.model = nullptr;
+                a.c.image = m->d_image;
+                a.c.weight = m->d_weight;
+                a.c.chimap = nullptr;
+                a.c.partial = m->d_partial;
+                a.c.row0 = (int)m->row0;
+                a.c.row1 = (int)m->row1;
+                a.c.ngroups = ngroups;
+                a.c.gpr = (int)div_up(m->width, 32);
+                a.c.mode = OUT_CHI2;
+                a.c.tail = Tail{ reduce_out, m->d_counter, scale };
+                a.objs = m->d_objs;
+                a.sync = m->d_sync;
+                a.conv_gx = test_giveup ? -1 : (int)conv_gx;
+                a.conv_blocks = (int)conv_blocks;
+                void* args[] = { &a };
+                rc = launch(m, m->f_point[idx], dim3((unsigned)grid), dim3(256), args, st);
+            }
+            else
+            {
+                PointArgsNoPsf a;
+                a.r = r;
+                a.objs = m->d_objs;
+                a.sync = m->d_sync;
+                a.conv_gx = test_giveup ? -1 : 0;
+                a.conv_blocks = 0;
+                void* args[] = { &a };
+                rc = launch(m, m->f_point[idx], dim3((unsigned)grid), dim3(256), args, st);
+            }
+            if(rc) return rc;
+            *reduced = true;
+            return LCU_OK;
+        }
+    }
     // set_params, src/nested.c:77
     if(!fold)
     {
@@ -522,6 +622,17 @@ int enqueue_batch(lcu_model* m, size_t nbatch, const float* d_params, double* d_
     return LCU_OK;
 }
 
+// a wait inside lcu_point_* timed out: leave its hand-over words clean and do not use it again
+int point_kernel_failed(lcu_model* m)
+{
+    RT_CHECK(cudaStreamSynchronize(m->stream));
+    m->point_off = true;
+    drop_point_graphs(m);
+    RT_CHECK(cudaMemset(m->d_sync, 0, 2*sizeof(unsigned)));
+    RT_CHECK(cudaMemset(m->d_counter, 0, m->maxb*sizeof(unsigned)));
+    return LCU_OK;
+}
+
 // (re)build the single-point graph if the launch configuration changed;
 // returns false when graphs are unavailable (the plain path is used then)
 bool single_point_graph(lcu_model* m)
@@ -563,6 +674,9 @@ bool single_point_graph(lcu_model* m)
             if(!mapped)
                 cudaGetLastError();
             const size_t po = (size_t)slot*m->npars;
+            // the one-kernel path is used only where the host can see that it gave up (the result
+            // word keeps its "pending" pattern): in graphs that write straight into mapped memory
+            m->point_ok = mapped && !getenv("LCU_NO_POLL");
             if(mapped)
                 ok = enqueue_batch(m, 1, dp + po, dl + slot, m->stream) == LCU_OK;
             else
@@ -571,6 +685,7 @@ bool single_point_graph(lcu_model* m)
                 ok = ok && enqueue_batch(m, 1, m->d_params + po, m->d_lnew + slot, m->stream) == LCU_OK;
                 ok = ok && cudaMemcpyAsync(m->h_lnew + slot, m->d_lnew + slot, sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
             }
+            m->point_ok = false;
             ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
         }
         // captured launches have not run: they count each time the graph is launched
@@ -609,7 +724,7 @@ void destroy_device_state(lcu_model* m)
         for(cudaEvent_t& e : es.e)
             cudaEventDestroy(e);
     m->evsets.clear();
-    void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_counter, m->d_params, m->d_lnew,
+    void* bufs[] = { m->d_image, m->d_weight, m->d_objs, m->d_raw, m->d_partial, m->d_counter, m->d_sync, m->d_params, m->d_lnew,
                      m->d_value1, m->d_error1, m->d_model1, m->d_chi1 };
     for(void* p : bufs)
         if(p) cudaFree(p);
@@ -867,6 +982,8 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
     {
         const char* fold_env = getenv("LCU_FOLD_SETTER");
         m->fold = fold_env && *fold_env == '1';
+        const char* point_env = getenv("LCU_FUSED_POINT");
+        m->point = point_env && *point_env == '1';
     }
     m->pair = !(desc->flags & LCU_NO_PAIR);
     for(const ModelObject& o : m->objs)
@@ -965,7 +1082,8 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
           << "#define LCU_MAXB " << m->maxb << "\n"
           << "#define LCU_OBJ_CONST " << (m->obj_const ? 1 : 0) << "\n"
           << "#define LCU_PAIR " << (m->pair ? 1 : 0) << "\n"
-          << "#define LCU_FOLD " << (m->fold ? 1 : 0) << "\n";
+          << "#define LCU_FOLD " << (m->fold ? 1 : 0) << "\n"
+          << "#define LCU_POINT " << (m->point ? 1 : 0) << "\n";
         if(pair_minblocks)
             s << "#define LCU_PAIR_MINBLOCKS " << pair_minblocks << "\n";
         s << "#include \"shim.cuh\"\n#include \"object.cuh\"\n\n";
@@ -1088,6 +1206,18 @@ int lcu_model_create(lcu_ctx* ctx, const lcu_object_spec* specs, size_t nobjs, c
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_q[3], m->mod, "lcu_render_q_s8")));
         M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_render_pair_err, m->mod, "lcu_render_pair_err")));
     }
+    if(m->point)
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_point[2], m->mod, "lcu_point_s4")));
+    if(m->point)
+        M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_point[3], m->mod, "lcu_point_s8")));
+    for(int i = 2; i < 4 && m->point; ++i)
+    {
+        int per_sm = 0;
+        M_CHECK(DRV_CHECK(drv.OccupancyMaxActiveBlocks(&per_sm, m->f_point[i], 256, 0)));
+        m->point_capacity[i] = (size_t)std::max(per_sm, 0)*(size_t)std::max(ctx->sm_count, 0);
+    }
+    M_CHECK(RT_CHECK(cudaMalloc(&m->d_sync, 2*sizeof(unsigned))));
+    M_CHECK(RT_CHECK(cudaMemset(m->d_sync, 0, 2*sizeof(unsigned))));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_reduce, m->mod, "lcu_reduce")));
     M_CHECK(DRV_CHECK(drv.ModuleGetFunction(&m->f_make_weight, m->mod, "lcu_make_weight")));
     if(m->has_psf)
@@ -1341,6 +1471,13 @@ int lcu_loglike_batch(lcu_model* m, size_t nbatch, const float* params, double* 
                     break;
             if(*word == pending)
                 RT_CHECK(cudaStreamSynchronize(m->stream));
+            if(*word == pending)
+            {
+                // the one-kernel path gave up waiting (its grid was not resident at once): never again on this model
+                rc = point_kernel_failed(m);
+                if(rc) return rc;
+                return lcu_loglike_batch(m, 1, params, lnew);
+            }
         }
         else
             RT_CHECK(cudaStreamSynchronize(m->stream));
@@ -1427,6 +1564,14 @@ int lcu_loglike_wait(lcu_model* m, int ticket, double* lnew)
         set_error("lcu_loglike_wait: no evaluation in flight under ticket %d", ticket);
         return LCU_E_ARG;
     }
+    if(m->async_redone[ticket])
+    {
+        // answered already while the other ticket was being redone (see below)
+        m->async_redone[ticket] = false;
+        m->async_busy[ticket] = false;
+        *lnew = m->async_redo[ticket];
+        return LCU_OK;
+    }
     volatile unsigned long long* word = reinterpret_cast<volatile unsigned long long*>(m->h_lnew + ticket);
     if(!getenv("LCU_NO_POLL"))
         for(unsigned spins = 1; *word == LCU_PENDING; ++spins)
@@ -1435,6 +1580,39 @@ int lcu_loglike_wait(lcu_model* m, int ticket, double* lnew)
     m->async_busy[ticket] = false;
     if(*word == LCU_PENDING)
         RT_CHECK(cudaEventSynchronize(m->async_done[ticket]));
+    if(*word == LCU_PENDING)
+    {
+        // The one-kernel path gave up waiting (its grid was not resident at once).  Redo every
+        // outstanding point the three-kernel way now; the other ticket's answer is kept for its wait.
+        RT_CHECK(cudaStreamSynchronize(m->stream));
+        const int other = 1 - ticket;
+        const bool other_busy = m->async_busy[other];
+        std::vector<float> p[2];
+        double done[2] = { m->h_lnew[0], m->h_lnew[1] };
+        bool pending[2];
+        for(int s = 0; s < 2; ++s)
+        {
+            p[s].assign(m->h_params + (size_t)s*m->npars, m->h_params + (size_t)(s + 1)*m->npars);
+            pending[s] = reinterpret_cast<volatile unsigned long long*>(m->h_lnew)[s] == LCU_PENDING;
+        }
+        rc = point_kernel_failed(m);
+        if(rc) return rc;
+        m->async_busy[other] = false;
+        rc = lcu_loglike_batch(m, 1, p[ticket].data(), lnew);
+        if(rc) return rc;
+        if(other_busy)
+        {
+            if(pending[other])
+            {
+                rc = lcu_loglike_batch(m, 1, p[other].data(), &done[other]);
+                if(rc) return rc;
+            }
+            m->async_redo[other] = done[other];
+            m->async_redone[other] = true;
+            m->async_busy[other] = true;
+        }
+        return LCU_OK;
+    }
     *lnew = m->h_lnew[ticket];
     if(m->profile)
         harvest_profile(m);

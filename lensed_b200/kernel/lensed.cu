@@ -149,7 +149,7 @@ __device__ __forceinline__ void lcu_reduce_block(int ngroups, const double* p, d
 
 // Called by every thread of every block of point b once the block's partials
 // are written: the block that finishes last adds them up, in lcu_reduce's shape.
-__device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsigned nblocks, int ngroups, const double* partial)
+__device__ __forceinline__ bool lcu_fused_reduce(const lcu_tail& t, int b, unsigned nblocks, int ngroups, const double* partial)
 {
     __shared__ bool last;
     __threadfence();
@@ -158,11 +158,12 @@ __device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsig
         last = atomicAdd(t.counter + b, 1u) == nblocks - 1;
     __syncthreads();
     if(!last)
-        return;
+        return false;
     __threadfence();
     if(threadIdx.x == 0)
         t.counter[b] = 0;
     lcu_reduce_block(ngroups, partial + (size_t)b*ngroups, t.scale, t.out + b);
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -181,17 +182,21 @@ __device__ __forceinline__ void lcu_fused_reduce(const lcu_tail& t, int b, unsig
 // halves the chain of dependent ray evaluations of a small launch (7 -> 4 for rule
 // g3k7 shared by 8 warps).  Each lane computes the one-ray bits, the values land
 // in the same shared-memory slots and are added up in the same order.
-template<int S, bool ERR, bool FOLD = false, bool PAIRQ = false>
-__device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
+// EXT (lcu_point_*: one kernel for all stages of a single point): the object
+// block and the block index come from the caller, the point is number 0 and the
+// caller runs the tail.
+template<int S, bool ERR, bool FOLD = false, bool PAIRQ = false, bool EXT = false>
+__device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a, const uint* ext_data = nullptr, unsigned ext_bx = 0)
 {
     constexpr int P = LCU_BLOCK/S;          // pixels per block
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int pg = warp/S;                  // 32-pixel group within the block
     const int ns = warp%S;                  // which share of the points
-    const int b = blockIdx.y;
+    const int b = EXT ? 0 : blockIdx.y;
+    const unsigned bx = EXT ? ext_bx : blockIdx.x;
 
-    const long long kk = (long long)blockIdx.x*P + pg*32 + lane;
+    const long long kk = (long long)bx*P + pg*32 + lane;
     const bool live = kk < a.nk;
     const long long k = a.k0 + (live ? kk : 0);
 
@@ -201,6 +206,9 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
     // split kernels -- those run on small images, where the extra copy node
     // would cost more than the block's 48 loads (single-point latency)
     const uint* data;
+    if constexpr(EXT)
+        data = ext_data;
+    else
 #if LCU_OBJ_CONST
     if constexpr(S == 1)
         data = reinterpret_cast<const uint*>(lcu_objs_c) + b*LCU_WORDS;
@@ -353,11 +361,11 @@ __device__ __forceinline__ void lcu_render_impl(const lcu_render_args& a)
 #pragma unroll
         for(int off = 16; off > 0; off >>= 1)
             s += __shfl_down_sync(0xffffffffu, s, off);
-        const long long g = ((long long)blockIdx.x*P + pg*32) >> 5;
+        const long long g = ((long long)bx*P + pg*32) >> 5;
         if(lane == 0 && g < a.ngroups)
             a.partial[(size_t)b*a.ngroups + g] = s;
     }
-    if constexpr(S > 1)
+    if constexpr(S > 1 && !EXT)
         if(a.tail.out)
             lcu_fused_reduce(a.tail, b, gridDim.x, a.ngroups, a.partial);
 }
@@ -670,16 +678,19 @@ lcu_convolve(const __grid_constant__ lcu_convolve_args a)
 #define LCU_CS_CW (LCU_CS_W + PSF_WIDTH - 1)
 #define LCU_CS_CH (LCU_CS_H + PSF_HEIGHT - 1)
 
-extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
-lcu_convolve_small(const __grid_constant__ lcu_convolve_args a)
+// EXT (lcu_point_*): tile indices from the caller, point 0, the rendered image
+// read past L1 (other blocks of the same kernel wrote it), the caller runs the tail.
+template<bool EXT>
+__device__ __forceinline__ void lcu_convolve_small_impl(const lcu_convolve_args& a, unsigned ext_bx = 0, unsigned ext_by = 0)
 {
     __shared__ float tile[LCU_CS_CH][LCU_CS_CW];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.z;
-    const int gx0 = blockIdx.x*LCU_CS_W;
-    const int gy0 = a.row0 + blockIdx.y*LCU_CS_H;
+    const int b = EXT ? 0 : blockIdx.z;
+    const unsigned bx = EXT ? ext_bx : blockIdx.x, by = EXT ? ext_by : blockIdx.y;
+    const int gx0 = bx*LCU_CS_W;
+    const int gy0 = a.row0 + by*LCU_CS_H;
 
     const float* raw = a.raw + (size_t)b*IMAGE_SIZE;
 
@@ -691,7 +702,7 @@ lcu_convolve_small(const __grid_constant__ lcu_convolve_args a)
         const int r = i/LCU_CS_CW, c = i%LCU_CS_CW;
         const int yy = min(max(cy + r, 0), IMAGE_HEIGHT - 1);
         const int xx = min(max(cx + c, 0), IMAGE_WIDTH - 1);
-        tile[r][c] = raw[(size_t)yy*IMAGE_WIDTH + xx];
+        tile[r][c] = EXT ? __ldcg(raw + (size_t)yy*IMAGE_WIDTH + xx) : raw[(size_t)yy*IMAGE_WIDTH + xx];
     }
     __syncthreads();
 
@@ -733,15 +744,151 @@ lcu_convolve_small(const __grid_constant__ lcu_convolve_args a)
             s += __shfl_sync(0xffffffffu, c, (lane & 24) + r);
         const double s01 = __shfl_sync(0xffffffffu, s, 0) + __shfl_sync(0xffffffffu, s, 8);
         const double s23 = __shfl_sync(0xffffffffu, s, 16) + __shfl_sync(0xffffffffu, s, 24);
-        const int g = blockIdx.x;
+        const int g = bx;
         if(lane == 0 && row_live && g < a.gpr)
             a.partial[(size_t)b*a.ngroups + (size_t)(gj - a.row0)*a.gpr + g] = s01 + s23;
     }
-    if(a.tail.out)
-        lcu_fused_reduce(a.tail, b, gridDim.x*gridDim.y, a.ngroups, a.partial);
+    if constexpr(!EXT)
+        if(a.tail.out)
+            lcu_fused_reduce(a.tail, b, gridDim.x*gridDim.y, a.ngroups, a.partial);
 }
 
+extern "C" __global__ void __launch_bounds__(LCU_BLOCK)
+lcu_convolve_small(const __grid_constant__ lcu_convolve_args a) { lcu_convolve_small_impl<false>(a); }
+
 #endif // PSF
+
+#if LCU_POINT
+// ---------------------------------------------------------------------------
+// One kernel for all stages of ONE point on a small image (the sampler's
+// one-point-per-call pattern): set_params -> render -> convolve + chi^2 -> sum,
+// what lcu_set_params, lcu_render[_q]_s{S}, lcu_convolve_small and the fused
+// final reduction do as three dependent launches, with the same device code in
+// the same order (the same bits) and two hand-overs through global memory instead
+// of two kernel boundaries:
+//   * block 0 runs set_params (one thread, as lcu_set_params does), publishes the
+//     object block and raises a flag; the other blocks wait for the flag;
+//   * every block renders its 32*8/S pixels; with a PSF it then takes a ticket:
+//     the LAST conv_blocks arrivers wait until all blocks have arrived and each
+//     convolves one 32 x 8 tile (the others are done); the last tile to finish
+//     adds the chi^2 partial sums up and stores the log-likelihood.
+// Progress: a block waits either for block 0's flag (block 0 is dispatched first)
+// or, as one of the last conv_blocks arrivers, for blocks that are running or
+// still to be dispatched -- at most conv_blocks blocks ever hold a slot while
+// they wait, and the host uses this kernel only when that is a small fraction
+// of what the device holds at once.  Every wait is nevertheless bounded by a
+// cycle count, after which the block gives up: the result word then keeps its
+// "pending" pattern and the host falls back to the three-kernel path for good.
+// Compiled only into models created with LCU_FUSED_POINT=1 in the environment:
+// measured, the two hand-overs cost what the two kernel boundaries cost (20.9 us
+// against 20.0 us per call on a 100 x 100 image).
+// ---------------------------------------------------------------------------
+struct lcu_point_args
+{
+    lcu_render_args r;          // r.objs unused (the object block is computed here), r.params = the point's parameters
+#if PSF
+    lcu_convolve_args c;
+#endif
+    uint* objs;                 // [LCU_WORDS] scratch: the point's object block, written by block 0
+    unsigned* sync;             // [2], zero between launches: object block ready, blocks that have rendered
+    int conv_gx, conv_blocks;   // convolution tiles per row / in total (0 without a PSF)
+};
+
+__device__ __forceinline__ unsigned lcu_ld_acquire(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// thread 0 of the block waits until *p >= target; false after ~2^26 cycles (tens of milliseconds)
+__device__ __forceinline__ bool lcu_wait_for(const unsigned* p, unsigned target)
+{
+    __shared__ int ok;
+    if(threadIdx.x == 0)
+    {
+        const long long t0 = clock64();
+        int good = 1;
+        while(lcu_ld_acquire(p) < target)
+            if(clock64() - t0 > (1ll << 26))
+            {
+                good = 0;
+                break;
+            }
+        ok = good;
+    }
+    __syncthreads();
+    return ok != 0;
+}
+
+template<int S, bool PAIRQ>
+__device__ __forceinline__ void lcu_point_impl(const lcu_point_args& a)
+{
+    __shared__ __align__(16) uint sdata[LCU_WORDS];
+    const unsigned G = gridDim.x;
+
+    // stage 1: the object block (src/nested.c:77)
+    if(blockIdx.x == 0)
+    {
+        __shared__ float sparams[LCU_NPARS > 0 ? LCU_NPARS : 1];
+        if(threadIdx.x < LCU_NPARS)
+            sparams[threadIdx.x] = a.r.params[threadIdx.x];
+        __syncthreads();
+        if(threadIdx.x == 0)
+            lcu_set_params_block(sdata, sparams);
+        __syncthreads();
+        for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+            a.objs[i] = sdata[i];
+        __threadfence();
+        __syncthreads();
+        if(threadIdx.x == 0 && a.conv_gx >= 0)     // conv_gx < 0: the host's test of the give-up path (the flag is never raised)
+            atomicExch(a.sync + 0, 1u);
+    }
+    else
+    {
+        if(!lcu_wait_for(a.sync + 0, 1u))
+            return;
+        for(int i = threadIdx.x; i < LCU_WORDS; i += LCU_BLOCK)
+            sdata[i] = __ldcg(a.objs + i);
+        __syncthreads();
+    }
+
+    // stage 2: render (src/nested.c:84); without a PSF the chi^2 terms are fused in
+    lcu_render_impl<S, false, false, PAIRQ, true>(a.r, sdata, blockIdx.x);
+
+#if PSF
+    // stage 3: the last conv_blocks blocks to get here convolve (src/nested.c:89-97)
+    __shared__ unsigned ticket;
+    __threadfence();
+    __syncthreads();
+    if(threadIdx.x == 0)
+        ticket = atomicAdd(a.sync + 1, 1u);
+    __syncthreads();
+    const unsigned first = G - (unsigned)a.conv_blocks;
+    if(ticket < first)
+        return;
+    if(!lcu_wait_for(a.sync + 1, G))
+        return;
+    const unsigned tile = ticket - first;
+    lcu_convolve_small_impl<true>(a.c, tile % (unsigned)a.conv_gx, tile / (unsigned)a.conv_gx);
+    const bool last = lcu_fused_reduce(a.c.tail, 0, (unsigned)a.conv_blocks, a.c.ngroups, a.c.partial);
+#else
+    const bool last = lcu_fused_reduce(a.r.tail, 0, G, a.r.ngroups, a.r.partial);
+#endif
+    // the block that stored the result leaves the hand-over words at zero for the next launch
+    if(last && threadIdx.x == 0)
+    {
+        a.sync[0] = 0;
+        a.sync[1] = 0;
+    }
+}
+
+#define LCU_POINT_KERNEL(S) \
+    extern "C" __global__ void __launch_bounds__(LCU_BLOCK, LCU_RENDER_MINBLOCKS) \
+    lcu_point_s##S(const __grid_constant__ lcu_point_args a) { lcu_point_impl<S, LCU_PAIR != 0>(a); }
+LCU_POINT_KERNEL(4)
+LCU_POINT_KERNEL(8)
+#endif // LCU_POINT
 
 // ---------------------------------------------------------------------------
 // data preparation: weight map from gain and offset (src/data.c:314-330), masked

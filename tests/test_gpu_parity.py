@@ -640,6 +640,59 @@ def test_single_point_graph_and_profile(gpu_ctx, monkeypatch):
     assert pr["render_ms"] > 0 and pr["convolve_ms"] > 0 and pr["reduce_ms"] >= 0 and pr["set_params_ms"] > 0
 
 
+@pytest.mark.parametrize("name", ["full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"])
+def test_one_kernel_point_path(gpu_ctx, monkeypatch, name):
+    """Opt-in (LCU_FUSED_POINT=1; measured ~1 us slower than the default, so an
+    experiment on record): one point of a small image with set_params, render,
+    convolve + chi^2 and the final sum in ONE kernel (lcu_point_s*), hand-overs
+    through global memory instead of kernel boundaries -- the bits of the three-kernel sequence and of
+    the batched path, one launch per evaluation, also with two in flight, after a
+    change of the row range, and over many evaluations (the hand-over words return
+    to zero every time).  A kernel that gives up waiting (forced here: block 0
+    never raises its flag) leaves the result word pending; the host then falls
+    back to the three-kernel sequence for good and still returns the right value."""
+    import lensed_b200 as L
+    cfg = H.example_config(name)
+    P = np.stack([cfg.params*(1 + 1e-3*i) for i in range(6)]).astype(np.float32)
+    nk = 3 if cfg.psf is not None else 2
+    m3 = cfg.product(gpu_ctx)
+    ref = m3.loglike_batch(np.repeat(P, 8, axis=0))[::8]
+    n0 = L.launch_count()
+    assert np.array_equal(np.array([m3.loglike(p) for p in P]), ref)
+    assert L.launch_count() - n0 == len(P)*nk
+    monkeypatch.setenv("LCU_FUSED_POINT", "1")               # opt-in: measured slower than the three launches
+    m = cfg.product(gpu_ctx)
+    n0 = L.launch_count()
+    assert np.array_equal(np.array([m.loglike(p) for p in P]), ref)
+    assert L.launch_count() - n0 == len(P)                    # one kernel per evaluation
+    assert np.array_equal(np.array([m.loglike(P[i % 6]) for i in range(300)]), np.tile(ref, 50))
+    t0, t1 = m.loglike_async(P[0]), m.loglike_async(P[1])
+    assert (m.loglike_wait(t0), m.loglike_wait(t1)) == (ref[0], ref[1])
+    assert np.array_equal(m.loglike_batch(P), ref)            # batches are unaffected
+    h = cfg.image.shape[0]
+    m.set_rows(7, h - 9)
+    m3.set_rows(7, h - 9)
+    assert m.loglike(P[2]) == m3.loglike(P[2]) != ref[2]
+    m.set_rows(0, h)
+    assert m.loglike(P[2]) == ref[2]
+    m.close(); m3.close()
+    # the give-up path
+    monkeypatch.setenv("LCU_POINT_TEST_TIMEOUT", "1")
+    mt = cfg.product(gpu_ctx)
+    assert mt.loglike(P[0]) == ref[0]                         # ~35 ms: every block's wait runs out, then the fallback
+    monkeypatch.delenv("LCU_POINT_TEST_TIMEOUT")
+    n0 = L.launch_count()
+    assert mt.loglike(P[1]) == ref[1] and L.launch_count() - n0 == nk       # three-kernel sequence from now on
+    mt.close()
+    monkeypatch.setenv("LCU_POINT_TEST_TIMEOUT", "1")
+    ma = cfg.product(gpu_ctx)
+    t0, t1 = ma.loglike_async(P[2]), ma.loglike_async(P[3])
+    assert ma.loglike_wait(t1) == ref[3] and ma.loglike_wait(t0) == ref[2]
+    monkeypatch.delenv("LCU_POINT_TEST_TIMEOUT")
+    assert ma.loglike(P[4]) == ref[4]
+    ma.close()
+
+
 @pytest.mark.parametrize("env", [None, "LCU_NO_GRAPH", "LCU_GRAPH_COPIES", "LCU_NO_POLL"])
 def test_async_pair_same_bits_two_in_flight(gpu_ctx, monkeypatch, env):
     """lcu_loglike_async / lcu_loglike_wait: two evaluations in flight, results

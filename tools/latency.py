@@ -15,9 +15,11 @@ ctx = L.Context(device=0, objects_dir=OBJECTS_DIR)
 for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
     cfg = H.example_config(name)
     res = {}
-    for mode in ("graph", "graph_one_point_per_pass", "graph_folded_set_params", "plain"):
-        for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR"):
+    for mode in ("graph", "graph_one_kernel", "graph_one_point_per_pass", "graph_folded_set_params", "plain"):
+        for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR", "LCU_FUSED_POINT"):
             os.environ.pop(env, None)
+        if mode == "graph_one_kernel":
+            os.environ["LCU_FUSED_POINT"] = "1"
         if mode == "plain":
             os.environ["LCU_NO_GRAPH"] = "1"
         elif mode == "graph_folded_set_params":
@@ -48,7 +50,8 @@ for name in ("full_mock_nopsf", "full_mock_psf", "test_sersic_bulge"):
         m.close()
     assert res["graph"]["lnew"] == res["plain"]["lnew"] == res["graph_folded_set_params"]["lnew"]
     assert res["graph"]["lnew"] == res["graph_one_point_per_pass"]["lnew"]
-    for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR"):
+    assert res["graph"]["lnew"] == res["graph_one_kernel"]["lnew"]
+    for env in ("LCU_NO_GRAPH", "LCU_FOLD_SETTER", "LCU_NO_SPLIT_PAIR", "LCU_FUSED_POINT"):
         os.environ.pop(env, None)
     try:
         from oracle import pyoracle as O
