@@ -57,6 +57,21 @@ def test_fixture_objects_are_the_reference_files():
         assert files == sorted(f for f in os.listdir(REF_OBJECTS) if f.endswith(".cl"))
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_OBJECTS), reason="reference tree not present")
+def test_same_device_code_from_the_reference_tree_and_from_the_fixture_directory():
+    """The program text and the sm_100a image of the C4 and C5 models are the same
+    bytes whether the plugin directory is /root/reference/objects or the committed
+    copy every GPU run uses: what the B200 ran is what the reference's files give."""
+    from lensed_b200 import workloads
+    img = np.zeros((64, 64), np.float32)
+    a, b = L.Context(device=-1, objects_dir=REF_OBJECTS), L.Context(device=-1, objects_dir=H.OBJECTS_DIR)
+    for w in (workloads.c4(64), workloads.c5(64)):
+        ma = L.Model(a, w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
+        mb = L.Model(b, w["objects"], img, img, rule=w["rule"], psf=w["psf"], flags=L.LCU_FAST_INTRINSICS | L.LCU_FAST_ATANH)
+        assert ma.source == mb.source and ma.cubin == mb.cubin and len(ma.cubin) > 0
+    a.close(); b.close()
+
+
 def test_library_ships_no_object_files(monkeypatch, tmp_path):
     """No objects_dir and no LENSED_PATH: the first object load fails in the
     reference's words (src/kernel.c:757-759); LENSED_PATH/objects is found as the
